@@ -1,0 +1,171 @@
+/* starrynight_b200.h -- C ABI of libstarrynight_b200.so
+ *
+ * B200-native (sm_100a) replacement for StarryNight's Metropolis Monte Carlo
+ * hot path and the lattice-wide observables that read the same state.
+ *
+ * The reference has no FFI: the path is reached by direct calls to file-static
+ * functions over globals inside one translation unit.
+ * Each entry point below names the reference call site / global it replaces.
+ * A driver written like /root/reference/src/starrynight-main.c calls
+ *     sn_create            where main() mallocs `lattice` and calls gen_neighbour()   (main.c:155-161,180)
+ *     sn_set_lattice       after initialise_lattice()/solid_solution()                (main.c:203-205)
+ *     sn_set_beta          where main() sets beta = 1/((float)T/300.0)                (main.c:215,239)
+ *     sn_mc_sweeps         where main() calls MC_moves(MCMinorSteps)                  (main.c:222,248)
+ *     sn_get_lattice / observables   where analysis_*() read `lattice`               (main.c:29-103)
+ *     sn_get_counters      where main() prints ACCEPT / REJECT                        (main.c:273)
+ *
+ * Conventions: every function returns 0 on success and a non-zero sn_status on
+ * failure; sn_last_error() returns a message for the calling thread's last
+ * failure.  The caller owns all host buffers; the handle owns all device
+ * memory.  One host thread per handle.  Calls are synchronous with respect to
+ * the host unless stated otherwise.  There is no CPU fallback: if no CUDA
+ * device is usable sn_create fails.
+ *
+ * Host lattice layout (everywhere): float[X][Y][nz][4] = (x, y, z, length),
+ * z fastest -- the memory order of the reference's `struct dipole
+ * lattice[x][y][z]` (config.c:32-36; main.c:155-161).  `nz` is the handle's own
+ * Z-slab (nz == Z unless the lattice is slab-decomposed across GPUs).
+ */
+#ifndef STARRYNIGHT_B200_H
+#define STARRYNIGHT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SN_API __attribute__((visibility("default")))
+#else
+#define SN_API
+#endif
+
+typedef struct sn_handle sn_handle;
+
+typedef enum {
+    SN_OK = 0,
+    SN_ERR_INVALID = 1,      /* bad argument */
+    SN_ERR_CUDA = 2,         /* CUDA runtime / driver error */
+    SN_ERR_UNSUPPORTED = 3,  /* configuration the library cannot run */
+    SN_ERR_NOMEM = 4
+} sn_status;
+
+/* arithmetic of the energy-audit entry points */
+typedef enum {
+    SN_PREC_F32 = 0,      /* the sweep kernel's own FP32 local-field arithmetic (1e-5 bar) */
+    SN_PREC_F64 = 1,      /* all-FP64, reference statement order (1e-12 bar vs the float->double reference build) */
+    SN_PREC_REPLICA = 2   /* float terms + double accumulation exactly as montecarlo-core.c:99-121 (bit-equal to the native reference) */
+} sn_precision;
+
+typedef enum {
+    SN_KERNEL_AUTO = 0,    /* tiled shared-memory kernel when the lattice allows it, else colour passes */
+    SN_KERNEL_COLOUR = 1,  /* one launch per colour sublattice, neighbours read from global memory */
+    SN_KERNEL_TILED = 2    /* TMA-staged shared-memory tiles (needs cutoff 3, X,Y,nz multiples of 32) */
+} sn_kernel;
+
+typedef struct {
+    int X, Y, Z;              /* global lattice, config.c:12-14 / cfg keys X Y Z */
+    int cutoff;               /* DipoleCutOff, config.c:70 */
+    double CageStrain;        /* config.c:68 */
+    double K;                 /* config.c:66 */
+    float Efield[3];          /* config.c:64, initial value for every replica */
+    double beta;              /* config.c:62, initial value for every replica */
+    int ConstrainToX;         /* config.c:85 */
+    int DIM;                  /* config.c:16 (2 => proposals on the XY circle) */
+    int nreplicas;            /* independent lattices advanced by one call (T / field sweeps, seeds) */
+    unsigned long long seed;  /* Philox key; replaces init_genrand(0xDEADBEEF+T), main.c:172-176 */
+    int device;               /* CUDA device ordinal */
+    int z0, nz;               /* this handle's Z-slab [z0, z0+nz) of the global lattice; nz = 0 means the whole Z */
+    int kernel;               /* sn_kernel */
+} sn_params;
+
+/* number of r^2 bins sn_rdf fills: r^2 = 0..80 (analysis.c:540-550) */
+#define SN_RDF_BINS 81
+
+SN_API const char *sn_last_error(void);
+SN_API const char *sn_version(void);
+
+/* fills *p with the reference's defaults (config.c:12-93): 20^3, cutoff 3, ... */
+SN_API int sn_default_params(sn_params *p);
+
+/* replaces: lattice malloc + gen_neighbour()  (main.c:155-161,180; montecarlo-core.c:38-72) */
+SN_API int sn_create(const sn_params *p, sn_handle **out);
+SN_API int sn_destroy(sn_handle *h);
+
+/* the neighbour list the handle built; dxyz has 3*n ints, d has n floats, in the
+ * reference's order (montecarlo-core.c:47-62).  Pass NULL arrays to query n. */
+SN_API int sn_neighbour_table(sn_handle *h, int *n, int *dxyz, float *d);
+
+/* replaces direct writes/reads of `lattice` (config.c:32-36).  host buffer:
+ * float[X][Y][nz][4].  H2D / D2H copies happen inside the call. */
+SN_API int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen);
+SN_API int sn_get_lattice(sn_handle *h, int replica, float *xyzlen);
+
+/* replaces assignments to the globals beta (main.c:215,239), Efield (config.c:132-134),
+ * CageStrain (main.c:149) between MC_moves calls */
+SN_API int sn_set_beta(sn_handle *h, int replica, double beta);
+SN_API int sn_set_efield(sn_handle *h, int replica, const float E[3]);
+SN_API int sn_set_cagestrain(sn_handle *h, double cagestrain);
+
+/* replaces MC_moves(X*Y*Z*nsweeps) (montecarlo-core.c:143-149; main.c:222,248).
+ * One sweep attempts one Metropolis update at every site of every replica, in
+ * colour-sublattice order; each attempt is a fresh full dE over the cut-off
+ * sphere (site_energy, montecarlo-core.c:76-141) followed by the accept test
+ * (montecarlo-core.c:179).  Returns after the work is queued on the handle's
+ * stream; any later call that reads results synchronises. */
+SN_API int sn_mc_sweeps(sn_handle *h, long long nsweeps);
+
+/* same, bracketed by CUDA events on the handle's stream: *ms = device time of
+ * the whole call, *launches = kernels launched.  Used by bench.py. */
+SN_API int sn_mc_sweeps_timed(sn_handle *h, long long nsweeps, double *ms, long long *launches);
+
+SN_API int sn_synchronize(sn_handle *h);
+
+/* replaces the globals ACCEPT / REJECT (config.c:26-27; montecarlo-core.c:187-190).
+ * vacant = attempts that hit a length==0 site, which the reference neither
+ * accepts nor rejects (montecarlo-core.c:163). */
+SN_API int sn_get_counters(sn_handle *h, int replica, unsigned long long *accept,
+                    unsigned long long *reject, unsigned long long *vacant);
+SN_API int sn_reset_counters(sn_handle *h);
+
+/* audit of site_energy (montecarlo-core.c:76-141): dE[i] of rotating site
+ * sites[3i..3i+2] = (x, y, zlocal) to newdip[3i..3i+2], lattice unchanged. */
+SN_API int sn_site_energy(sn_handle *h, int replica, int precision, int n, const int *sites,
+                   const float *newdip, double *dE);
+
+/* total lattice energy, defined so that site_energy is its exact single-site
+ * difference (the reference has none: main.c:63).  out = {E_dd, E_cage, E_field, E_K}
+ *   E_dd   = 1/2 sum_i sum_j l_i l_j [p_i.p_j - 3 (n.p_i)(n.p_j)] / d^3
+ *   E_cage = -1/2 CageStrain sum_i sum_nn p_i.p_j
+ *   E_field= sum_i p_i.E            E_K = -K sum_i (|p_ix| + |p_iy|)  [K > 0]
+ * For a slab handle the sums run over the handle's own sites. */
+SN_API int sn_total_energy(sn_handle *h, int replica, int precision, double out[4]);
+
+/* replaces polarisation() (analysis.c:48-62): P = (1/N) sum_i p_i, all three components */
+SN_API int sn_polarisation(sn_handle *h, int replica, double P[3]);
+/* replaces landau_order() (analysis.c:506-526): |sum_i p_i|^2 / N * N as written there */
+SN_API int sn_landau_order(sn_handle *h, int replica, double *landau);
+/* replaces radial_order_parameter() (analysis.c:528-598): accumulated sums and
+ * counts per r^2 = 0..80 BEFORE the division at :587-588, in FP64 / int64 */
+SN_API int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum, long long *count);
+/* replaces dipole_potential() over the lattice (analysis.c:65-94,264-308): V[X][Y][nz] */
+SN_API int sn_potential_map(sn_handle *h, int replica, double *V);
+
+/* ---- Z-slab decomposition across GPUs (one handle per GPU) ------------------
+ * A slab handle keeps `cutoff` ghost planes below and above its own planes.
+ * sn_get_boundary / sn_set_ghost move them through host memory (bootstrap and
+ * CPU tests); sn_ipc_* wire the device-to-device path used by sn_mc_sweeps. */
+/* side 0 = lowest `cutoff` own planes, 1 = highest; buffer float[X][Y][cutoff][4] */
+SN_API int sn_get_boundary(sn_handle *h, int replica, int side, float *planes);
+/* side 0 = ghost planes below z0 (the lower neighbour's top planes), 1 = above */
+SN_API int sn_set_ghost(sn_handle *h, int replica, int side, const float *planes);
+/* 64-byte CUDA IPC handles of the lattice buffer and the phase-flag buffer */
+SN_API int sn_ipc_export(sn_handle *h, void *lattice_handle64, void *flags_handle64);
+/* attach the neighbour that owns the planes below (side 0) / above (side 1) */
+SN_API int sn_ipc_attach(sn_handle *h, int side, const void *lattice_handle64, const void *flags_handle64);
+/* same wiring for two handles living in one process (peer access is enabled) */
+SN_API int sn_attach_peer(sn_handle *h, int side, sn_handle *peer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARRYNIGHT_B200_H */

@@ -1,0 +1,274 @@
+"""starrynight_b200 -- host-side mirror of libstarrynight_b200.so (ctypes).
+
+The product is the C-ABI library (include/starrynight_b200.h) and the C driver
+(driver/); this module is the thin Python binding the tests and bench.py use.
+It mirrors the reference's operations for the hot path with the reference's
+names (MC_moves, site_energy, polarisation, landau_order,
+radial_order_parameter, dipole_potential) so the parity tests read like calls
+into /root/reference/src/starrynight-*.c.
+
+There is no CPU path here: loading fails loudly when the shared library has not
+been built, and ``Simulation(...)`` fails loudly when no CUDA device is usable.
+Nothing in this package imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstarrynight_b200.so")
+
+SN_PREC_F32, SN_PREC_F64, SN_PREC_REPLICA = 0, 1, 2
+SN_KERNEL_AUTO, SN_KERNEL_COLOUR, SN_KERNEL_TILED = 0, 1, 2
+SN_RDF_BINS = 81
+
+EXPORTS = [
+    "sn_last_error", "sn_version", "sn_default_params", "sn_create", "sn_destroy", "sn_neighbour_table",
+    "sn_set_lattice", "sn_get_lattice", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_mc_sweeps",
+    "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_site_energy",
+    "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_get_boundary",
+    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer",
+]
+
+
+class SnError(RuntimeError):
+    pass
+
+
+class sn_params(C.Structure):
+    _fields_ = [("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int), ("cutoff", C.c_int),
+                ("CageStrain", C.c_double), ("K", C.c_double), ("Efield", C.c_float * 3),
+                ("beta", C.c_double), ("ConstrainToX", C.c_int), ("DIM", C.c_int),
+                ("nreplicas", C.c_int), ("seed", C.c_ulonglong), ("device", C.c_int),
+                ("z0", C.c_int), ("nz", C.c_int), ("kernel", C.c_int)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SnError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(make -C starrynight_b200/csrc). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.sn_last_error.restype = C.c_char_p
+    lib.sn_version.restype = C.c_char_p
+    H = C.c_void_p
+    lib.sn_create.argtypes = [C.POINTER(sn_params), C.POINTER(H)]
+    lib.sn_destroy.argtypes = [H]
+    lib.sn_neighbour_table.argtypes = [H, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    lib.sn_set_lattice.argtypes = [H, C.c_int, C.c_void_p]
+    lib.sn_get_lattice.argtypes = [H, C.c_int, C.c_void_p]
+    lib.sn_set_beta.argtypes = [H, C.c_int, C.c_double]
+    lib.sn_set_efield.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
+    lib.sn_set_cagestrain.argtypes = [H, C.c_double]
+    lib.sn_mc_sweeps.argtypes = [H, C.c_longlong]
+    lib.sn_mc_sweeps_timed.argtypes = [H, C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.sn_synchronize.argtypes = [H]
+    lib.sn_get_counters.argtypes = [H, C.c_int] + [C.POINTER(C.c_ulonglong)] * 3
+    lib.sn_reset_counters.argtypes = [H]
+    lib.sn_site_energy.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sn_total_energy.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.sn_polarisation.argtypes = [H, C.c_int, C.POINTER(C.c_double)]
+    lib.sn_landau_order.argtypes = [H, C.c_int, C.POINTER(C.c_double)]
+    lib.sn_rdf.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sn_potential_map.argtypes = [H, C.c_int, C.c_void_p]
+    lib.sn_get_boundary.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    lib.sn_set_ghost.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    lib.sn_ipc_export.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.sn_ipc_attach.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
+    lib.sn_attach_peer.argtypes = [H, C.c_int, H]
+    _lib = lib
+    return lib
+
+
+def default_params() -> sn_params:
+    p = sn_params()
+    _check(load_library().sn_default_params(C.byref(p)))
+    return p
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SnError(f"libstarrynight_b200 error {rc}: {load_library().sn_last_error().decode()}")
+
+
+def beta_of_T(T: float) -> float:
+    """beta = 1/((float)T/300.0), main.c:215 (T = 0 gives +inf, as in the reference)."""
+    t = float(np.float32(T)) / 300.0
+    return float("inf") if t == 0.0 else 1.0 / t
+
+
+class Simulation:
+    """One device-resident lattice (or a batch of replicas, or one Z-slab of a
+    larger lattice).  Method names follow the reference functions they replace."""
+
+    def __init__(self, X, Y, Z, DipoleCutOff=3, CageStrain=1.0, K=0.0, Efield=(0.0, 0.0, 0.0), beta=1.0,
+                 ConstrainToX=False, DIM=3, nreplicas=1, seed=0xDEADBEEF + 300, device=0, z0=0, nz=0,
+                 kernel=SN_KERNEL_AUTO):
+        self.lib = load_library()
+        p = default_params()
+        p.X, p.Y, p.Z, p.cutoff = X, Y, Z, DipoleCutOff
+        p.CageStrain, p.K, p.beta = CageStrain, K, beta
+        for i in range(3):
+            p.Efield[i] = float(Efield[i])
+        p.ConstrainToX, p.DIM, p.nreplicas = int(ConstrainToX), DIM, nreplicas
+        p.seed, p.device, p.z0, p.nz, p.kernel = seed, device, z0, nz, kernel
+        self.params = p
+        self.X, self.Y, self.Z = X, Y, Z
+        self.nz = nz if nz > 0 else Z
+        self.nreplicas = nreplicas
+        self.h = C.c_void_p()
+        _check(self.lib.sn_create(C.byref(p), C.byref(self.h)))
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.sn_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def nsites(self):
+        return self.X * self.Y * self.nz
+
+    # -- gen_neighbour (montecarlo-core.c:38)
+    def neighbours(self):
+        n = C.c_int(0)
+        _check(self.lib.sn_neighbour_table(self.h, C.byref(n), None, None))
+        dxyz = np.zeros((n.value, 3), np.int32)
+        d = np.zeros(n.value, np.float32)
+        _check(self.lib.sn_neighbour_table(self.h, C.byref(n), dxyz.ctypes.data, d.ctypes.data))
+        return dxyz, d
+
+    # -- lattice[x][y][z] (config.c:32-36)
+    def set_lattice(self, lat, replica=0):
+        a = np.ascontiguousarray(lat, np.float32)
+        if a.size != self.nsites * 4:
+            raise SnError(f"set_lattice: expected {self.X}x{self.Y}x{self.nz}x4 floats, got {a.shape}")
+        _check(self.lib.sn_set_lattice(self.h, replica, a.ctypes.data))
+
+    def get_lattice(self, replica=0, out=None):
+        a = out if out is not None else np.empty((self.X, self.Y, self.nz, 4), np.float32)
+        _check(self.lib.sn_get_lattice(self.h, replica, a.ctypes.data))
+        return a
+
+    def set_lattice_ptr(self, ptr, replica=0):
+        """Host pointer variant (e.g. a pinned torch tensor's data_ptr())."""
+        _check(self.lib.sn_set_lattice(self.h, replica, C.c_void_p(ptr)))
+
+    def get_lattice_ptr(self, ptr, replica=0):
+        _check(self.lib.sn_get_lattice(self.h, replica, C.c_void_p(ptr)))
+
+    def set_beta(self, beta, replica=0):
+        _check(self.lib.sn_set_beta(self.h, replica, float(beta)))
+
+    def set_T(self, T, replica=0):
+        self.set_beta(beta_of_T(T), replica)
+
+    def set_efield(self, E, replica=0):
+        e = (C.c_float * 3)(*[float(v) for v in E])
+        _check(self.lib.sn_set_efield(self.h, replica, e))
+
+    def set_cagestrain(self, c):
+        _check(self.lib.sn_set_cagestrain(self.h, float(c)))
+
+    # -- MC_moves (montecarlo-core.c:143): one sweep = X*Y*Z attempts
+    def MC_sweeps(self, nsweeps=1):
+        _check(self.lib.sn_mc_sweeps(self.h, int(nsweeps)))
+
+    def MC_sweeps_timed(self, nsweeps=1):
+        ms, n = C.c_double(0), C.c_longlong(0)
+        _check(self.lib.sn_mc_sweeps_timed(self.h, int(nsweeps), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def synchronize(self):
+        _check(self.lib.sn_synchronize(self.h))
+
+    def counters(self, replica=0):
+        a, r, v = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+        _check(self.lib.sn_get_counters(self.h, replica, C.byref(a), C.byref(r), C.byref(v)))
+        return a.value, r.value, v.value
+
+    def reset_counters(self):
+        _check(self.lib.sn_reset_counters(self.h))
+
+    # -- site_energy (montecarlo-core.c:76)
+    def site_energy(self, sites, newdip, precision=SN_PREC_F64, replica=0):
+        s = np.ascontiguousarray(sites, np.int32).reshape(-1, 3)
+        nd = np.ascontiguousarray(newdip, np.float32).reshape(-1, 3)
+        if len(s) != len(nd):
+            raise SnError("site_energy: sites and newdip differ in length")
+        out = np.zeros(len(s), np.float64)
+        _check(self.lib.sn_site_energy(self.h, replica, precision, len(s), s.ctypes.data, nd.ctypes.data, out.ctypes.data))
+        return out
+
+    def total_energy(self, precision=SN_PREC_F64, replica=0):
+        out = (C.c_double * 4)()
+        _check(self.lib.sn_total_energy(self.h, replica, precision, out))
+        return np.array(list(out))
+
+    # -- analysis.c
+    def polarisation(self, replica=0):
+        out = (C.c_double * 3)()
+        _check(self.lib.sn_polarisation(self.h, replica, out))
+        return np.array(list(out))
+
+    def landau_order(self, replica=0):
+        out = C.c_double(0)
+        _check(self.lib.sn_landau_order(self.h, replica, C.byref(out)))
+        return out.value
+
+    def radial_order_parameter(self, replica=0):
+        fe = np.zeros(SN_RDF_BINS, np.float64)
+        afe = np.zeros(SN_RDF_BINS, np.float64)
+        cnt = np.zeros(SN_RDF_BINS, np.int64)
+        _check(self.lib.sn_rdf(self.h, replica, fe.ctypes.data, afe.ctypes.data, cnt.ctypes.data))
+        return fe, afe, cnt
+
+    def dipole_potential(self, replica=0):
+        v = np.zeros(self.nsites, np.float64)
+        _check(self.lib.sn_potential_map(self.h, replica, v.ctypes.data))
+        return v.reshape(self.X, self.Y, self.nz)
+
+    # -- Z-slab plumbing
+    def get_boundary(self, side, replica=0):
+        g = self.params.cutoff
+        a = np.empty((self.X, self.Y, g, 4), np.float32)
+        _check(self.lib.sn_get_boundary(self.h, replica, side, a.ctypes.data))
+        return a
+
+    def set_ghost(self, side, planes, replica=0):
+        a = np.ascontiguousarray(planes, np.float32)
+        _check(self.lib.sn_set_ghost(self.h, replica, side, a.ctypes.data))
+
+    def ipc_export(self):
+        a, b = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+        _check(self.lib.sn_ipc_export(self.h, a, b))
+        return bytes(a), bytes(b)
+
+    def ipc_attach(self, side, lattice_handle: bytes, flags_handle: bytes):
+        a = (C.c_ubyte * 64).from_buffer_copy(lattice_handle)
+        b = (C.c_ubyte * 64).from_buffer_copy(flags_handle)
+        _check(self.lib.sn_ipc_attach(self.h, side, a, b))
+
+    def attach_peer(self, side, peer: "Simulation"):
+        _check(self.lib.sn_attach_peer(self.h, side, peer.h))

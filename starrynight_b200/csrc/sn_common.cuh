@@ -1,0 +1,150 @@
+// sn_common.cuh -- shared definitions for libstarrynight_b200.so (sm_100a only)
+//
+// Device lattice layout ("padded AoS"): one float4 (x, y, z, length) per site --
+// the reference's `struct dipole` (config.c:32-36) -- in an array of
+// (X+2g) x (Y+2g) x (nz+2g) float4 per replica, z fastest, where g = cutoff is a
+// ghost shell that mirrors the periodic images (and, for a Z-slab handle, the
+// neighbouring GPUs' boundary planes).  Every kernel that walks the cut-off
+// sphere therefore addresses neighbours as base + constant offset, with none of
+// the reference's `(X+x+dx)%X` arithmetic (montecarlo-core.c:97).  Whoever
+// changes a site within g of a face also writes its ghost images.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/starrynight_b200.h"
+
+#define SN_MAX_NB 1024          // neighbour-table capacity in constant memory (cutoff <= 6)
+
+struct SnGeom {
+    int X, Y, Z;                // global lattice
+    int z0, nz;                 // this handle's slab
+    int g;                      // ghost width in x and y (= cutoff)
+    int gz;                     // ghost width in z (0 when Z == 1: the axis does not interact)
+    int PY, PZ;                 // padded extents of y and z
+    long long sx, sy;           // strides (in sites) of x and y in the padded array
+    long long rep_stride;       // sites per replica in the padded array
+    int periodic_z;             // nz == Z: z ghosts are periodic images of this handle's own planes
+};
+
+__host__ __device__ inline long long sn_pidx(const SnGeom &G, int x, int y, int z)
+{
+    return ((long long)(x + G.g) * G.PY + (y + G.g)) * G.PZ + (z + G.gz);
+}
+
+// One colour sublattice per axis.  Period P = cutoff+1; if the extent is not a
+// multiple of P the r = extent % P trailing coordinates get colours of their
+// own, so same-colour sites are always > cutoff apart, also across the wrap.
+struct SnAxisColour {
+    int P, n, r, ncol;          // period, extent, remainder, number of colours
+};
+
+__host__ __device__ inline SnAxisColour sn_axis_colour(int extent, int cutoff, bool flat)
+{
+    SnAxisColour a;
+    a.n = extent;
+    if (flat) { a.P = 1; a.r = 0; a.ncol = 1; return a; }      // axis does not interact (Z==1)
+    a.P = cutoff + 1;
+    if (extent < a.P) { a.P = extent; a.r = 0; a.ncol = extent; return a; }
+    a.r = extent % a.P;
+    a.ncol = a.P + a.r;
+    return a;
+}
+__host__ __device__ inline int sn_axis_count(const SnAxisColour &a, int c)
+{
+    return c < a.P ? (a.n - a.r) / a.P : 1;
+}
+__host__ __device__ inline int sn_axis_coord(const SnAxisColour &a, int c, int i)
+{
+    return c < a.P ? c + a.P * i : a.n - a.r + (c - a.P);
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based per-site RNG --------
+// replaces the global MT19937 stream (mt19937ar-cok.c) the reference draws from
+// in MC_move (montecarlo-core.c:159-161,179) and random_sphere_point (config.c:209-210).
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ inline Philox4 sn_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                    uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// 24-bit uniform on [0,1)
+__host__ __device__ inline float sn_u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+
+#define SN_CUDA_CHECK(call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return sn_fail(SN_ERR_CUDA, "%s: %s (%s:%d)", #call,           \
+                                              cudaGetErrorString(e_), __FILE__, __LINE__);    \
+    } while (0)
+
+int sn_fail(int code, const char *fmt, ...);
+
+// neighbour entry for the table-driven (any cutoff) path
+struct SnNbEntry {
+    int dx, dy, dz, nn;                 // nn = 1 for |r| == 1 (cage-strain neighbours)
+    float txx, tyy, tzz, txy, txz, tyz; // (delta_ab - 3 n_a n_b) / d^3
+};
+
+struct sn_handle {
+    sn_params p;
+    SnGeom G;
+    float4 *lat = nullptr;              // device, nreplicas * rep_stride
+    float *beta = nullptr;              // device, per replica
+    float4 *efield = nullptr;           // device, per replica
+    unsigned long long *counters = nullptr;   // device, per replica {accept, reject, vacant}
+    unsigned long long sweep = 0;       // sweeps done so far (Philox counter word)
+    cudaStream_t stream = nullptr;
+    int nnb = 0;
+    std::vector<int> nb_dxyz;           // reference order (montecarlo-core.c:47-62)
+    std::vector<float> nb_d;
+    SnNbEntry *nb_table = nullptr;      // device copy for the table-driven kernels
+    int *d_nb_dxyz = nullptr;           // device copy of nb_dxyz for the exact-order audit kernels
+    std::vector<float> h_beta;          // host mirrors of the per-replica couplings
+    std::vector<float> h_efield;        // 3 per replica
+    bool species = true;                // false when every length is exactly 1 (skips the l_j multiplies)
+    std::vector<char> rep_species;      // per replica: some length != 1
+    bool use_tiled = false;
+    // slab wiring
+    float4 *peer_lat[2] = {nullptr, nullptr};       // lower / upper neighbour's padded lattice
+    unsigned int *flags = nullptr;                  // own phase flags (device)
+    unsigned int *peer_flags[2] = {nullptr, nullptr};
+    unsigned int phase_epoch = 0;
+    bool peer_is_ipc[2] = {false, false};
+    unsigned char ipc_key[2][64] = {};
+    int num_sms = 148;
+    void *tmap = nullptr;               // CUtensorMap storage for the tiled kernel (device-constant copy made at launch)
+    // scratch
+    double *d_scratch = nullptr; size_t scratch_bytes = 0;
+    void *staging = nullptr; size_t staging_bytes = 0;
+};
+
+// entry points implemented across translation units
+int sn_sweep_colour_launch(sn_handle *h, long long nsweeps, long long *launches);
+int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches);
+bool sn_tiled_supported(const sn_handle *h, std::string *why);
+int sn_tiled_prepare(sn_handle *h);
+void sn_tiled_release(sn_handle *h);
+int sn_refresh_ghosts(sn_handle *h);
+int sn_energy_exact_launch(sn_handle *h, int replica, int precision, int n, const int *d_sites,
+                           const float *d_newdip, double *d_out);
+int sn_energy_exact_map_launch(sn_handle *h, int replica, int precision, int which, double *d_out);
+int sn_scratch(sn_handle *h, size_t bytes, void **out);

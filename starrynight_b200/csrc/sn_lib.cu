@@ -1,0 +1,570 @@
+// sn_lib.cu -- C ABI of libstarrynight_b200.so (see include/starrynight_b200.h)
+//
+// Host runtime around the sm_100a kernels: owns the padded device lattice, the
+// per-replica couplings, the Philox key/counter, the stream, and dispatches
+// sn_mc_sweeps to the colour-pass kernel (sn_sweep_colour.cuh) or the
+// TMA/shared-memory tile kernel (sn_sweep_tiled.cuh).  There is no CPU path.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "sn_common.cuh"
+#include "sn_field.cuh"
+#include "sn_observables.cuh"
+#include "sn_sweep_colour.cuh"
+#include "sn_sweep_tiled.cuh"
+
+static thread_local char sn_err[512] = "";
+static int sn_slab_phase_sync(sn_handle *h, long long *launches);
+
+int sn_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(sn_err, sizeof sn_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *sn_last_error(void) { return sn_err; }
+extern "C" const char *sn_version(void) { return "starrynight_b200 0.1 (sm_100a)"; }
+
+extern "C" int sn_default_params(sn_params *p)
+{
+    if (!p) return sn_fail(SN_ERR_INVALID, "sn_default_params: null");
+    memset(p, 0, sizeof *p);
+    p->X = 20; p->Y = 20; p->Z = 20;          // config.c:12-14
+    p->cutoff = 3;                            // config.c:70
+    p->CageStrain = 1.0; p->K = 1.0;          // config.c:66-68
+    p->beta = 1.0;                            // config.c:62
+    p->ConstrainToX = 0; p->DIM = 3;          // config.c:85,16
+    p->nreplicas = 1;
+    p->seed = 0xDEADBEEFull + 300;            // main.c:172
+    p->device = 0; p->z0 = 0; p->nz = 0;
+    p->kernel = SN_KERNEL_AUTO;
+    return SN_OK;
+}
+
+int sn_scratch(sn_handle *h, size_t bytes, void **out)
+{
+    if (bytes > h->scratch_bytes) {
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        h->d_scratch = nullptr; h->scratch_bytes = 0;
+        SN_CUDA_CHECK(cudaMalloc(&h->d_scratch, bytes));
+        h->scratch_bytes = bytes;
+    }
+    *out = h->d_scratch;
+    return SN_OK;
+}
+
+// gen_neighbour(), montecarlo-core.c:38-72: order dx -> dy -> dz, 0 < d <= cutoff,
+// d = sqrt in float; ZCutOff = 0 when Z == 1.
+static void sn_build_neighbours(sn_handle *h)
+{
+    const int c = h->p.cutoff, zc = h->p.Z == 1 ? 0 : c;
+    h->nb_dxyz.clear(); h->nb_d.clear();
+    std::vector<SnNbEntry> tab;
+    for (int dx = -c; dx <= c; dx++) for (int dy = -c; dy <= c; dy++) for (int dz = -zc; dz <= zc; dz++) {
+        if (!dx && !dy && !dz) continue;
+        const float d = (float)sqrt((double)((float)dx * dx + dy * dy + dz * dz));
+        if (d > (float)c) continue;
+        h->nb_dxyz.push_back(dx); h->nb_dxyz.push_back(dy); h->nb_dxyz.push_back(dz);
+        h->nb_d.push_back(d);
+        const double r2 = (double)dx * dx + (double)dy * dy + (double)dz * dz, dd = sqrt(r2), i3 = 1.0 / (dd * dd * dd);
+        SnNbEntry e;
+        e.dx = dx; e.dy = dy; e.dz = dz; e.nn = (dx * dx + dy * dy + dz * dz) == 1;
+        e.txx = (float)(i3 - 3.0 * dx * dx * i3 / r2); e.tyy = (float)(i3 - 3.0 * dy * dy * i3 / r2);
+        e.tzz = (float)(i3 - 3.0 * dz * dz * i3 / r2);
+        e.txy = (float)(-3.0 * dx * dy * i3 / r2); e.txz = (float)(-3.0 * dx * dz * i3 / r2); e.tyz = (float)(-3.0 * dy * dz * i3 / r2);
+        tab.push_back(e);
+    }
+    h->nnb = (int)h->nb_d.size();
+    cudaMalloc(&h->nb_table, sizeof(SnNbEntry) * std::max(1, h->nnb));
+    cudaMemcpy(h->nb_table, tab.data(), sizeof(SnNbEntry) * h->nnb, cudaMemcpyHostToDevice);
+    cudaMalloc(&h->d_nb_dxyz, sizeof(int) * 3 * std::max(1, h->nnb));
+    cudaMemcpy(h->d_nb_dxyz, h->nb_dxyz.data(), sizeof(int) * 3 * h->nnb, cudaMemcpyHostToDevice);
+}
+
+static int sn_mode(const sn_handle *h) { return h->p.cutoff == 3 ? (h->p.Z == 1 ? 1 : 0) : 2; }
+
+extern "C" int sn_create(const sn_params *p, sn_handle **out)
+{
+    if (!p || !out) return sn_fail(SN_ERR_INVALID, "sn_create: null argument");
+    *out = nullptr;
+    if (p->X < 1 || p->Y < 1 || p->Z < 1) return sn_fail(SN_ERR_INVALID, "sn_create: lattice %dx%dx%d", p->X, p->Y, p->Z);
+    if (p->cutoff < 0 || p->cutoff > 6) return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: DipoleCutOff %d outside 0..6", p->cutoff);
+    if (p->nreplicas < 1) return sn_fail(SN_ERR_INVALID, "sn_create: nreplicas %d", p->nreplicas);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return sn_fail(SN_ERR_CUDA, "sn_create: no CUDA device (this library has no CPU path)");
+    if (p->device < 0 || p->device >= ndev) return sn_fail(SN_ERR_INVALID, "sn_create: device %d of %d", p->device, ndev);
+    SN_CUDA_CHECK(cudaSetDevice(p->device));
+
+    sn_handle *h = new sn_handle();
+    h->p = *p;
+    if (h->p.nz <= 0) { h->p.nz = p->Z; h->p.z0 = 0; }
+    if (h->p.z0 < 0 || h->p.z0 + h->p.nz > p->Z) { delete h; return sn_fail(SN_ERR_INVALID, "sn_create: slab [%d,%d) outside Z=%d", h->p.z0, h->p.z0 + h->p.nz, p->Z); }
+    SnGeom &G = h->G;
+    G.X = p->X; G.Y = p->Y; G.Z = p->Z; G.z0 = h->p.z0; G.nz = h->p.nz;
+    G.g = p->cutoff; G.gz = p->Z == 1 ? 0 : p->cutoff;
+    G.PY = G.Y + 2 * G.g; G.PZ = G.nz + 2 * G.gz;
+    G.sy = G.PZ; G.sx = (long long)G.PY * G.PZ;
+    G.rep_stride = (long long)(G.X + 2 * G.g) * G.sx;
+    G.periodic_z = (G.nz == G.Z);
+    if (!G.periodic_z) {
+        const int P = p->cutoff + 1;
+        if (G.nz % P || G.z0 % P || G.Z % P || G.nz < p->cutoff) {
+            delete h;
+            return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: Z-slabs need z0, nz and Z to be multiples of cutoff+1 (z0=%d nz=%d Z=%d)", G.z0, G.nz, G.Z);
+        }
+    }
+    cudaDeviceProp prop;
+    SN_CUDA_CHECK(cudaGetDeviceProperties(&prop, p->device));
+    h->num_sms = prop.multiProcessorCount;
+    SN_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t cells = (size_t)G.rep_stride * p->nreplicas;
+    if (cudaMalloc(&h->lat, cells * sizeof(float4)) != cudaSuccess) {
+        cudaGetLastError(); cudaStreamDestroy(h->stream); delete h;
+        return sn_fail(SN_ERR_NOMEM, "sn_create: cannot allocate %.1f MB for the lattice", cells * 16.0 / 1e6);
+    }
+    SN_CUDA_CHECK(cudaMemsetAsync(h->lat, 0, cells * sizeof(float4), h->stream));
+    SN_CUDA_CHECK(cudaMalloc(&h->beta, sizeof(float) * p->nreplicas));
+    SN_CUDA_CHECK(cudaMalloc(&h->efield, sizeof(float4) * p->nreplicas));
+    SN_CUDA_CHECK(cudaMalloc(&h->counters, sizeof(unsigned long long) * 3 * p->nreplicas));
+    SN_CUDA_CHECK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long) * 3 * p->nreplicas, h->stream));
+    SN_CUDA_CHECK(cudaMalloc(&h->flags, sizeof(unsigned int) * 64));
+    SN_CUDA_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(unsigned int) * 64, h->stream));
+    h->h_beta.assign(p->nreplicas, (float)p->beta);
+    h->rep_species.assign(p->nreplicas, 0);
+    h->species = false;
+    h->h_efield.resize(3 * (size_t)p->nreplicas);
+    std::vector<float4> e4(p->nreplicas);
+    for (int r = 0; r < p->nreplicas; r++) {
+        for (int k = 0; k < 3; k++) h->h_efield[3 * r + k] = p->Efield[k];
+        e4[r] = make_float4(p->Efield[0], p->Efield[1], p->Efield[2], 0.f);
+    }
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->beta, h->h_beta.data(), sizeof(float) * p->nreplicas, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->efield, e4.data(), sizeof(float4) * p->nreplicas, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    sn_build_neighbours(h);
+    SN_CUDA_CHECK(cudaGetLastError());
+
+    std::string why;
+    const bool can_tile = sn_tiled_supported(h, &why);
+    if (p->kernel == SN_KERNEL_TILED && !can_tile) {
+        sn_destroy(h);
+        return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: tiled kernel unavailable: %s", why.c_str());
+    }
+    h->use_tiled = can_tile && p->kernel != SN_KERNEL_COLOUR;
+    if (h->use_tiled) { int rc = sn_tiled_prepare(h); if (rc) { sn_destroy(h); return rc; } }
+    *out = h;
+    return SN_OK;
+}
+
+extern "C" int sn_destroy(sn_handle *h)
+{
+    if (!h) return SN_OK;
+    cudaSetDevice(h->p.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    sn_tiled_release(h);
+    for (int s = 0; s < 2; s++) if (h->peer_is_ipc[s]) {
+        if (h->peer_lat[s] && !(s == 1 && h->peer_lat[1] == h->peer_lat[0])) cudaIpcCloseMemHandle(h->peer_lat[s]);
+        if (h->peer_flags[s] && !(s == 1 && h->peer_flags[1] == h->peer_flags[0])) cudaIpcCloseMemHandle(h->peer_flags[s]);
+    }
+    cudaFree(h->lat); cudaFree(h->beta); cudaFree(h->efield); cudaFree(h->counters); cudaFree(h->flags);
+    cudaFree(h->nb_table); cudaFree(h->d_nb_dxyz); cudaFree(h->d_scratch); cudaFree(h->staging);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SN_OK;
+}
+
+extern "C" int sn_neighbour_table(sn_handle *h, int *n, int *dxyz, float *d)
+{
+    if (!h || !n) return sn_fail(SN_ERR_INVALID, "sn_neighbour_table: null");
+    *n = h->nnb;
+    if (dxyz) memcpy(dxyz, h->nb_dxyz.data(), sizeof(int) * 3 * h->nnb);
+    if (d) memcpy(d, h->nb_d.data(), sizeof(float) * h->nnb);
+    return SN_OK;
+}
+
+#define SN_CHECK_HANDLE(h, rep)                                                                        \
+    do {                                                                                               \
+        if (!(h)) return sn_fail(SN_ERR_INVALID, "%s: null handle", __func__);                        \
+        if ((rep) < 0 || (rep) >= (h)->p.nreplicas) return sn_fail(SN_ERR_INVALID, "%s: replica %d of %d", __func__, (rep), (h)->p.nreplicas); \
+        SN_CUDA_CHECK(cudaSetDevice((h)->p.device));                                                   \
+    } while (0)
+
+int sn_refresh_ghosts(sn_handle *h)
+{
+    const long long n = h->G.rep_stride;
+    dim3 grid((unsigned)((n + 255) / 256), h->p.nreplicas);
+    sn_refresh_ghosts_kernel<<<grid, 256, 0, h->stream>>>(h->lat, h->G);
+    SN_CUDA_CHECK(cudaGetLastError());
+    return SN_OK;
+}
+
+// strided copy between the host's dense [X][Y][nz] float4 block and the padded device array
+static int sn_copy_block(sn_handle *h, int replica, float *host, bool to_device)
+{
+    const SnGeom &G = h->G;
+    cudaMemcpy3DParms c;
+    memset(&c, 0, sizeof c);
+    float4 *dev = h->lat + (long long)replica * G.rep_stride + sn_pidx(G, 0, 0, 0);
+    cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)G.nz * 16, (size_t)G.nz * 16, G.Y);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)G.PZ * 16, (size_t)G.PZ * 16, G.PY);
+    c.srcPtr = to_device ? hp : dp; c.dstPtr = to_device ? dp : hp;
+    c.extent = make_cudaExtent((size_t)G.nz * 16, G.Y, G.X);
+    c.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    SN_CUDA_CHECK(cudaMemcpy3DAsync(&c, h->stream));
+    return SN_OK;
+}
+
+extern "C" int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_set_lattice: null buffer");
+    int rc = sn_copy_block(h, replica, const_cast<float *>(xyzlen), true);
+    if (rc) return rc;
+    if ((rc = sn_refresh_ghosts(h))) return rc;
+    // does any replica carry species (length != 1)?  decides the kernel specialisation
+    {
+        const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+        bool nonunit = false;
+        for (long long i = 0; i < n; i++) if (xyzlen[4 * i + 3] != 1.0f) { nonunit = true; break; }
+        h->rep_species[replica] = nonunit;
+        h->species = false;
+        for (int r = 0; r < h->p.nreplicas; r++) h->species = h->species || h->rep_species[r];
+    }
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+extern "C" int sn_get_lattice(sn_handle *h, int replica, float *xyzlen)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_get_lattice: null buffer");
+    int rc = sn_copy_block(h, replica, xyzlen, false);
+    if (rc) return rc;
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+extern "C" int sn_set_beta(sn_handle *h, int replica, double beta)
+{
+    SN_CHECK_HANDLE(h, replica);
+    h->h_beta[replica] = (float)beta;
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->beta + replica, &h->h_beta[replica], sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+extern "C" int sn_set_efield(sn_handle *h, int replica, const float E[3])
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!E) return sn_fail(SN_ERR_INVALID, "sn_set_efield: null");
+    for (int k = 0; k < 3; k++) h->h_efield[3 * replica + k] = E[k];
+    const float4 e4 = make_float4(E[0], E[1], E[2], 0.f);
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->efield + replica, &e4, sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+extern "C" int sn_set_cagestrain(sn_handle *h, double cagestrain)
+{
+    SN_CHECK_HANDLE(h, 0);
+    h->p.CageStrain = cagestrain;
+    return SN_OK;
+}
+
+extern "C" int sn_synchronize(sn_handle *h)
+{
+    SN_CHECK_HANDLE(h, 0);
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+// ---- sweeps -----------------------------------------------------------------
+static SnSweepArgs sn_sweep_args(sn_handle *h)
+{
+    SnSweepArgs a;
+    a.lat = h->lat; a.G = h->G;
+    a.ax = sn_axis_colour(h->G.X, h->p.cutoff, false);
+    a.ay = sn_axis_colour(h->G.Y, h->p.cutoff, false);
+    a.az = sn_axis_colour(h->G.nz, h->p.cutoff, h->G.Z == 1);
+    a.beta = h->beta; a.efield = h->efield;
+    a.cage = (float)h->p.CageStrain; a.K = (float)h->p.K;
+    a.constrain = h->p.ConstrainToX; a.dim = h->p.DIM;
+    a.counters = h->counters;
+    a.key0 = (uint32_t)h->p.seed; a.key1 = (uint32_t)(h->p.seed >> 32);
+    a.sweep_lo = (uint32_t)h->sweep; a.sweep_hi = (uint32_t)(h->sweep >> 32);
+    a.nb = h->nb_table; a.nnb = h->nnb;
+    a.peer_lo = h->peer_lat[0]; a.peer_hi = h->peer_lat[1];
+    return a;
+}
+
+template <int MODE, bool SPECIES>
+static void sn_launch_colour(const SnSweepArgs &a, int nrep, int cx, int cy, int cz, cudaStream_t st)
+{
+    const long long total = (long long)sn_axis_count(a.ax, cx) * sn_axis_count(a.ay, cy) * sn_axis_count(a.az, cz);
+    dim3 grid((unsigned)((total + 127) / 128), nrep);
+    sn_colour_pass_kernel<MODE, SPECIES><<<grid, 128, 0, st>>>(a, cx, cy, cz);
+}
+
+int sn_sweep_colour_launch(sn_handle *h, long long nsweeps, long long *launches)
+{
+    const int mode = sn_mode(h);
+    for (long long s = 0; s < nsweeps; s++) {
+        SnSweepArgs a = sn_sweep_args(h);
+        for (int cx = 0; cx < a.ax.ncol; cx++) for (int cy = 0; cy < a.ay.ncol; cy++) for (int cz = 0; cz < a.az.ncol; cz++) {
+            if (mode == 0) { if (h->species) sn_launch_colour<0, true>(a, h->p.nreplicas, cx, cy, cz, h->stream); else sn_launch_colour<0, false>(a, h->p.nreplicas, cx, cy, cz, h->stream); }
+            else if (mode == 1) { if (h->species) sn_launch_colour<1, true>(a, h->p.nreplicas, cx, cy, cz, h->stream); else sn_launch_colour<1, false>(a, h->p.nreplicas, cx, cy, cz, h->stream); }
+            else sn_launch_colour<2, true>(a, h->p.nreplicas, cx, cy, cz, h->stream);
+            if (launches) (*launches)++;
+            if (!h->G.periodic_z) { int rc = sn_slab_phase_sync(h, launches); if (rc) return rc; }
+        }
+        h->sweep++;
+    }
+    SN_CUDA_CHECK(cudaGetLastError());
+    return SN_OK;
+}
+
+static int sn_sweeps_impl(sn_handle *h, long long nsweeps, long long *launches)
+{
+    if (nsweeps < 0) return sn_fail(SN_ERR_INVALID, "sn_mc_sweeps: nsweeps %lld", nsweeps);
+    if (!h->G.periodic_z && (!h->peer_lat[0] || !h->peer_lat[1]))
+        return sn_fail(SN_ERR_INVALID, "sn_mc_sweeps: Z-slab handle has no neighbours attached (sn_ipc_attach / sn_attach_peer)");
+    return h->use_tiled ? sn_sweep_tiled_launch(h, nsweeps, launches) : sn_sweep_colour_launch(h, nsweeps, launches);
+}
+
+extern "C" int sn_mc_sweeps(sn_handle *h, long long nsweeps)
+{
+    SN_CHECK_HANDLE(h, 0);
+    return sn_sweeps_impl(h, nsweeps, nullptr);
+}
+
+extern "C" int sn_mc_sweeps_timed(sn_handle *h, long long nsweeps, double *ms, long long *launches)
+{
+    SN_CHECK_HANDLE(h, 0);
+    cudaEvent_t e0, e1;
+    SN_CUDA_CHECK(cudaEventCreate(&e0));
+    SN_CUDA_CHECK(cudaEventCreate(&e1));
+    long long n = 0;
+    SN_CUDA_CHECK(cudaEventRecord(e0, h->stream));
+    int rc = sn_sweeps_impl(h, nsweeps, &n);
+    SN_CUDA_CHECK(cudaEventRecord(e1, h->stream));
+    SN_CUDA_CHECK(cudaEventSynchronize(e1));
+    float t = 0.f;
+    SN_CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms) *ms = t;
+    if (launches) *launches = n;
+    return rc;
+}
+
+extern "C" int sn_get_counters(sn_handle *h, int replica, unsigned long long *accept, unsigned long long *reject,
+                               unsigned long long *vacant)
+{
+    SN_CHECK_HANDLE(h, replica);
+    unsigned long long c[3];
+    SN_CUDA_CHECK(cudaMemcpyAsync(c, h->counters + 3 * replica, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (accept) *accept = c[0];
+    if (reject) *reject = c[1];
+    if (vacant) *vacant = c[2];
+    return SN_OK;
+}
+
+extern "C" int sn_reset_counters(sn_handle *h)
+{
+    SN_CHECK_HANDLE(h, 0);
+    SN_CUDA_CHECK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long) * 3 * h->p.nreplicas, h->stream));
+    return SN_OK;
+}
+
+// ---- energy audit -------------------------------------------------------------
+static SnTerms sn_terms(const sn_handle *h, int replica)
+{
+    SnTerms t;
+    t.cage = (float)h->p.CageStrain; t.K = (float)h->p.K; t.beta = h->h_beta[replica];
+    t.E = make_float3(h->h_efield[3 * replica], h->h_efield[3 * replica + 1], h->h_efield[3 * replica + 2]);
+    t.constrain = h->p.ConstrainToX; t.dim = h->p.DIM;
+    return t;
+}
+
+extern "C" int sn_site_energy(sn_handle *h, int replica, int precision, int n, const int *sites, const float *newdip, double *dE)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (n < 0 || (n > 0 && (!sites || !newdip || !dE))) return sn_fail(SN_ERR_INVALID, "sn_site_energy: bad arguments");
+    if (precision < SN_PREC_F32 || precision > SN_PREC_REPLICA) return sn_fail(SN_ERR_INVALID, "sn_site_energy: precision %d", precision);
+    if (n == 0) return SN_OK;
+    for (int i = 0; i < n; i++)
+        if (sites[3 * i] < 0 || sites[3 * i] >= h->G.X || sites[3 * i + 1] < 0 || sites[3 * i + 1] >= h->G.Y || sites[3 * i + 2] < 0 || sites[3 * i + 2] >= h->G.nz)
+            return sn_fail(SN_ERR_INVALID, "sn_site_energy: site %d (%d,%d,%d) outside the lattice", i, sites[3 * i], sites[3 * i + 1], sites[3 * i + 2]);
+    const size_t bs = (size_t)n * 3 * sizeof(int), bn = (size_t)n * 3 * sizeof(float), bo = (size_t)n * sizeof(double);
+    void *s; int rc = sn_scratch(h, bs + bn + bo + 64, &s);
+    if (rc) return rc;
+    double *d_out = (double *)s;
+    int *d_sites = (int *)((char *)s + bo);
+    float *d_new = (float *)((char *)s + bo + bs);
+    SN_CUDA_CHECK(cudaMemcpyAsync(d_sites, sites, bs, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaMemcpyAsync(d_new, newdip, bn, cudaMemcpyHostToDevice, h->stream));
+    if (precision == SN_PREC_F32) {
+        const float4 *lat = h->lat + (long long)replica * h->G.rep_stride;
+        const SnTerms t = sn_terms(h, replica);
+        const int gs = (n + 127) / 128, mode = sn_mode(h);
+        if (mode == 0) sn_site_energy_f32_kernel<0, true><<<gs, 128, 0, h->stream>>>(lat, h->G, h->nb_table, h->nnb, t, n, d_sites, d_new, d_out);
+        else if (mode == 1) sn_site_energy_f32_kernel<1, true><<<gs, 128, 0, h->stream>>>(lat, h->G, h->nb_table, h->nnb, t, n, d_sites, d_new, d_out);
+        else sn_site_energy_f32_kernel<2, true><<<gs, 128, 0, h->stream>>>(lat, h->G, h->nb_table, h->nnb, t, n, d_sites, d_new, d_out);
+        SN_CUDA_CHECK(cudaGetLastError());
+    } else if ((rc = sn_energy_exact_launch(h, replica, precision, n, d_sites, d_new, d_out))) return rc;
+    SN_CUDA_CHECK(cudaMemcpyAsync(dE, d_out, bo, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+static int sn_reduce_to_host(sn_handle *h, const double *d_partials, int nblocks, int nv, double *out)
+{
+    std::vector<double> hp((size_t)nblocks * nv);
+    SN_CUDA_CHECK(cudaMemcpyAsync(hp.data(), d_partials, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < nv; k++) { double s = 0.0; for (int b = 0; b < nblocks; b++) s += hp[(size_t)b * nv + k]; out[k] = s; }
+    return SN_OK;
+}
+
+extern "C" int sn_total_energy(sn_handle *h, int replica, int precision, double out[4])
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!out) return sn_fail(SN_ERR_INVALID, "sn_total_energy: null");
+    if (precision < SN_PREC_F32 || precision > SN_PREC_REPLICA) return sn_fail(SN_ERR_INVALID, "sn_total_energy: precision %d", precision);
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
+    int rc;
+    if (precision == SN_PREC_F32) {
+        void *s; if ((rc = sn_scratch(h, sizeof(double) * 4 * nblocks, &s))) return rc;
+        const float4 *lat = h->lat + (long long)replica * h->G.rep_stride;
+        const SnTerms t = sn_terms(h, replica);
+        const int mode = sn_mode(h);
+        if (mode == 0) sn_energy_f32_kernel<0, true><<<nblocks, 256, 0, h->stream>>>(lat, h->G, h->nb_table, h->nnb, t.cage, t.K, t.E, (double *)s);
+        else if (mode == 1) sn_energy_f32_kernel<1, true><<<nblocks, 256, 0, h->stream>>>(lat, h->G, h->nb_table, h->nnb, t.cage, t.K, t.E, (double *)s);
+        else sn_energy_f32_kernel<2, true><<<nblocks, 256, 0, h->stream>>>(lat, h->G, h->nb_table, h->nnb, t.cage, t.K, t.E, (double *)s);
+        SN_CUDA_CHECK(cudaGetLastError());
+        if ((rc = sn_reduce_to_host(h, (double *)s, nblocks, 4, out))) return rc;
+    } else {
+        void *s; if ((rc = sn_scratch(h, sizeof(double) * (n + nblocks), &s))) return rc;
+        double *map = (double *)s, *part = map + n;
+        for (int k = 0; k < 4; k++) {
+            if ((rc = sn_energy_exact_map_launch(h, replica, precision, 1 << k, map))) return rc;
+            sn_sum_doubles_kernel<<<nblocks, 256, 0, h->stream>>>(map, n, part);
+            SN_CUDA_CHECK(cudaGetLastError());
+            if ((rc = sn_reduce_to_host(h, part, nblocks, 1, out + k))) return rc;
+        }
+    }
+    out[0] *= 0.5; out[1] *= 0.5;       // pair terms are counted from both ends
+    return SN_OK;
+}
+
+// ---- observables --------------------------------------------------------------
+static int sn_dipole_sum(sn_handle *h, int replica, double S[3])
+{
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
+    void *s; int rc = sn_scratch(h, sizeof(double) * 3 * nblocks, &s);
+    if (rc) return rc;
+    sn_sum_dipoles_kernel<<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, (double *)s);
+    SN_CUDA_CHECK(cudaGetLastError());
+    return sn_reduce_to_host(h, (double *)s, nblocks, 3, S);
+}
+
+extern "C" int sn_polarisation(sn_handle *h, int replica, double P[3])
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!P) return sn_fail(SN_ERR_INVALID, "sn_polarisation: null");
+    int rc = sn_dipole_sum(h, replica, P);
+    if (rc) return rc;
+    const double n = (double)h->G.X * h->G.Y * h->G.nz;    // analysis.c:60
+    for (int k = 0; k < 3; k++) P[k] /= n;
+    return SN_OK;
+}
+
+extern "C" int sn_landau_order(sn_handle *h, int replica, double *landau)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!landau) return sn_fail(SN_ERR_INVALID, "sn_landau_order: null");
+    double S[3];
+    int rc = sn_dipole_sum(h, replica, S);
+    if (rc) return rc;
+    const double n = (double)h->G.X * h->G.Y * h->G.nz;
+    *landau = (S[0] * S[0] + S[1] * S[1] + S[2] * S[2]) / n * n;   // analysis.c:523, as written
+    return SN_OK;
+}
+
+extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum, long long *count)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!fe_sum || !afe_sum || !count) return sn_fail(SN_ERR_INVALID, "sn_rdf: null");
+    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_rdf: not available on a Z-slab handle (radius-9 halo)");
+    const int CUT = 9;                              // analysis.c:540
+    std::vector<SnRdfOffset> off;
+    for (int dx = -CUT; dx <= CUT; dx++) for (int dy = -CUT; dy <= CUT; dy++) for (int dz = -CUT; dz <= CUT; dz++) {
+        const int r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 >= SN_RDF_BINS) continue;            // r^2 == 81 is neither zeroed nor printed by the reference
+        SnRdfOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.r2 = (short)r2;
+        off.push_back(o);
+    }
+    std::stable_sort(off.begin(), off.end(), [](const SnRdfOffset &a, const SnRdfOffset &b) { return a.r2 < b.r2; });
+    std::vector<int> first(SN_RDF_BINS + 1, 0);
+    for (auto &o : off) first[o.r2 + 1]++;
+    for (int b = 0; b < SN_RDF_BINS; b++) first[b + 1] += first[b];
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const int nblocks = (int)((n + 255) / 256);
+    const size_t b_off = off.size() * sizeof(SnRdfOffset), b_first = first.size() * sizeof(int);
+    const size_t b_out = sizeof(double) * 2 * SN_RDF_BINS * (size_t)nblocks;
+    void *s; int rc = sn_scratch(h, b_out + b_off + b_first + 256, &s);
+    if (rc) return rc;
+    double *d_out = (double *)s;
+    SnRdfOffset *d_off = (SnRdfOffset *)((char *)s + b_out);
+    int *d_first = (int *)((char *)s + b_out + ((b_off + 15) / 16) * 16);
+    SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaMemcpyAsync(d_first, first.data(), b_first, cudaMemcpyHostToDevice, h->stream));
+    sn_rdf_kernel<<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, d_first, SN_RDF_BINS, d_out);
+    SN_CUDA_CHECK(cudaGetLastError());
+    std::vector<double> tot(2 * SN_RDF_BINS);
+    if ((rc = sn_reduce_to_host(h, d_out, nblocks, 2 * SN_RDF_BINS, tot.data()))) return rc;
+    for (int b = 0; b < SN_RDF_BINS; b++) {
+        fe_sum[b] = tot[2 * b]; afe_sum[b] = tot[2 * b + 1];
+        count[b] = (long long)(first[b + 1] - first[b]) * n;       // analysis.c:578, one count per (site, offset)
+    }
+    return SN_OK;
+}
+
+extern "C" int sn_potential_map(sn_handle *h, int replica, double *V)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!V) return sn_fail(SN_ERR_INVALID, "sn_potential_map: null");
+    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_potential_map: not available on a Z-slab handle (radius-6 halo)");
+    const int MAXR = 6;                             // analysis.c:68
+    std::vector<SnPotOffset> off;
+    for (int dx = -MAXR; dx <= MAXR; dx++) for (int dy = -MAXR; dy <= MAXR; dy++) for (int dz = -MAXR; dz <= MAXR; dz++) {
+        if (!dx && !dy && !dz) continue;
+        const double d = sqrt((double)(dx * dx + dy * dy + dz * dz));
+        if (d > (double)MAXR) continue;
+        SnPotOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.pad = 0; o.w = 1.0 / (d * d * d);
+        off.push_back(o);
+    }
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const size_t b_v = sizeof(double) * n, b_off = off.size() * sizeof(SnPotOffset);
+    void *s; int rc = sn_scratch(h, b_v + b_off + 64, &s);
+    if (rc) return rc;
+    double *d_v = (double *)s;
+    SnPotOffset *d_off = (SnPotOffset *)((char *)s + ((b_v + 15) / 16) * 16);
+    SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));
+    sn_potential_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), d_v);
+    SN_CUDA_CHECK(cudaGetLastError());
+    SN_CUDA_CHECK(cudaMemcpyAsync(V, d_v, b_v, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+#include "sn_slab.cuh"

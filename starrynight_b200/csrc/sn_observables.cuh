@@ -1,0 +1,187 @@
+// sn_observables.cuh -- lattice-wide observables as warp-shuffle + block reductions.
+//
+// Replaces the serial loops of starrynight-analysis.c:
+//   polarisation()            :48-62     sum_i p_i                       -> sn_sum_dipoles_kernel
+//   landau_order()            :506-526   |sum_i p_i|^2                   -> same sums, finished on the host
+//   radial_order_parameter()  :528-598   FE / AFE correlations by r^2    -> sn_rdf_kernel
+//   dipole_potential()        :65-94     V_i = sum_j l_j p_j.r / d^3     -> sn_potential_kernel
+// and the lattice energy the reference never finished (main.c:63)        -> sn_energy_f32_kernel.
+// Accumulation is FP64 (int64 for counts): the reference's float sums and int
+// counts stop being sound beyond ~128^3.
+// Partial sums are written per block and added in a fixed order, so results are
+// bit-reproducible run to run.
+#pragma once
+
+#include "sn_field.cuh"
+
+__device__ __forceinline__ double sn_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of NV doubles per thread; result valid in thread 0
+template <int NV, int BLOCK>
+__device__ __forceinline__ void sn_block_sum(double (&v)[NV], double *smem /* NV * BLOCK/32 */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        v[k] = sn_warp_sum(v[k]);
+        if (lane == 0) smem[k * (BLOCK / 32) + warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double t = lane < BLOCK / 32 ? smem[k * (BLOCK / 32) + lane] : 0.0;
+            v[k] = sn_warp_sum(t);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void sn_site_of(const SnGeom &G, long long i, int &x, int &y, int &z)
+{
+    z = (int)(i % G.nz); y = (int)((i / G.nz) % G.Y); x = (int)(i / ((long long)G.nz * G.Y));
+}
+
+// out[block][3] = partial sum of p over the block's sites (grid-stride)
+__global__ void __launch_bounds__(256) sn_sum_dipoles_kernel(const float4 *__restrict__ lat, const SnGeom G, double *__restrict__ out)
+{
+    __shared__ double sm[3 * 8];
+    const long long n = (long long)G.X * G.Y * G.nz;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int x, y, z; sn_site_of(G, i, x, y, z);
+        const float4 p = lat[sn_pidx(G, x, y, z)];
+        v[0] += p.x; v[1] += p.y; v[2] += p.z;
+    }
+    sn_block_sum<3, 256>(v, sm);
+    if (threadIdx.x == 0) { out[3 * blockIdx.x] = v[0]; out[3 * blockIdx.x + 1] = v[1]; out[3 * blockIdx.x + 2] = v[2]; }
+}
+
+// generic deterministic reduction of n doubles into gridDim.x partials
+__global__ void __launch_bounds__(256) sn_sum_doubles_kernel(const double *__restrict__ in, long long n, double *__restrict__ out)
+{
+    __shared__ double sm[8];
+    double v[1] = {0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v[0] += in[i];
+    sn_block_sum<1, 256>(v, sm);
+    if (threadIdx.x == 0) out[blockIdx.x] = v[0];
+}
+
+// Lattice energy in the sweep kernel's own FP32 arithmetic (SN_PREC_F32):
+// per site e_dd = l_i p_i.F_i, e_cage = -Cs p_i.G_i, e_field = p_i.E, e_K.
+// out[block][4] partial sums (un-halved).
+template <int MODE, bool SPECIES>
+__global__ void __launch_bounds__(256) sn_energy_f32_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnNbEntry *__restrict__ nb,
+                                                            int nnb, float cage, float K, float3 E, double *__restrict__ out)
+{
+    __shared__ double sm[4 * 8];
+    const long long n = (long long)G.X * G.Y * G.nz;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int x, y, z; sn_site_of(G, i, x, y, z);
+        const float4 *site = lat + sn_pidx(G, x, y, z);
+        const float4 p = *site;
+        float3 F = make_float3(0.f, 0.f, 0.f), Gc = make_float3(0.f, 0.f, 0.f);
+        const long long sx = G.sx, sy = G.sy;
+        auto load = [&](int dx, int dy, int dz) { return site[dx * sx + dy * sy + dz]; };
+        if constexpr (MODE == 0) sn_local_field_cut3<false, SPECIES>(load, F, Gc);
+        else if constexpr (MODE == 1) sn_local_field_cut3<true, SPECIES>(load, F, Gc);
+        else sn_local_field_table(nb, nnb, load, F, Gc);
+        v[0] += p.w * (p.x * F.x + p.y * F.y + p.z * F.z);
+        v[1] += -cage * (p.x * Gc.x + p.y * Gc.y + p.z * Gc.z);
+        v[2] += p.x * E.x + p.y * E.y + p.z * E.z;
+        if (K > 0.0f) v[3] += -K * (fabsf(p.x) + fabsf(p.y));
+    }
+    sn_block_sum<4, 256>(v, sm);
+    if (threadIdx.x == 0) for (int k = 0; k < 4; k++) out[4 * blockIdx.x + k] = v[k];
+}
+
+// SN_PREC_F32 audit of single trial moves: the sweep kernel's own dE
+template <int MODE, bool SPECIES>
+__global__ void __launch_bounds__(128) sn_site_energy_f32_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnNbEntry *__restrict__ nb,
+                                                                 int nnb, SnTerms t, int n, const int *__restrict__ sites,
+                                                                 const float *__restrict__ newdip, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *site = lat + sn_pidx(G, sites[3 * i], sites[3 * i + 1], sites[3 * i + 2]);
+    const float4 old = *site;
+    float3 F = make_float3(0.f, 0.f, 0.f), Gc = make_float3(0.f, 0.f, 0.f);
+    const long long sx = G.sx, sy = G.sy;
+    auto load = [&](int dx, int dy, int dz) { return site[dx * sx + dy * sy + dz]; };
+    if constexpr (MODE == 0) sn_local_field_cut3<false, SPECIES>(load, F, Gc);
+    else if constexpr (MODE == 1) sn_local_field_cut3<true, SPECIES>(load, F, Gc);
+    else sn_local_field_table(nb, nnb, load, F, Gc);
+    out[i] = (double)sn_delta_e(old, make_float3(newdip[3 * i], newdip[3 * i + 1], newdip[3 * i + 2]), F, Gc, t);
+}
+
+// ---- radial order parameter (analysis.c:528-598) ------------------------------
+// Offsets inside the radius-9 sphere are sorted by r^2 on the host; `first[b]`
+// is the first offset of bin b.  Each thread walks every offset for its site,
+// keeps the running FE / AFE sums of the current bin in registers, and the block
+// reduces them once per bin -> out[block][bin][2].
+struct SnRdfOffset { short dx, dy, dz, r2; };
+
+__global__ void __launch_bounds__(256) sn_rdf_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnRdfOffset *__restrict__ off,
+                                                     const int *__restrict__ first, int nbins, double *__restrict__ out)
+{
+    __shared__ double sm[2 * 8];
+    const long long n = (long long)G.X * G.Y * G.nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    int x = 0, y = 0, z = 0;
+    if (live) sn_site_of(G, i, x, y, z);
+    const float4 a = live ? lat[sn_pidx(G, x, y, z)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < nbins; b++) {
+        double v[2] = {0.0, 0.0};
+        const int e = first[b + 1];
+        for (int o = first[b]; o < e && live; o++) {
+            const SnRdfOffset f = off[o];
+            int xx = (x + f.dx) % G.X, yy = (y + f.dy) % G.Y, zz = (z + f.dz) % G.nz;
+            if (xx < 0) xx += G.X;
+            if (yy < 0) yy += G.Y;
+            if (zz < 0) zz += G.nz;
+            const float4 c = lat[sn_pidx(G, xx, yy, zz)];
+            const double fe = (double)a.x * c.x + (double)a.y * c.y + (double)a.z * c.z;
+            double afe = fe;
+            if (f.r2 > 0) {
+                const double na = (double)f.dx * a.x + (double)f.dy * a.y + (double)f.dz * a.z;
+                const double nc = (double)f.dx * c.x + (double)f.dy * c.y + (double)f.dz * c.z;
+                afe = fe - 3.0 * na * nc / (double)f.r2;
+            } else afe = fe - 3.0 * 0.0;       // d forced to 1, n = 0 (analysis.c:571-573)
+            v[0] += fe; v[1] += afe;
+        }
+        if (e > first[b]) {                    // uniform across the block
+            sn_block_sum<2, 256>(v, sm);
+            if (threadIdx.x == 0) { out[((long long)blockIdx.x * nbins + b) * 2] = v[0]; out[((long long)blockIdx.x * nbins + b) * 2 + 1] = v[1]; }
+        } else if (threadIdx.x == 0) { out[((long long)blockIdx.x * nbins + b) * 2] = 0.0; out[((long long)blockIdx.x * nbins + b) * 2 + 1] = 0.0; }
+    }
+}
+
+// ---- electrostatic potential map (analysis.c:65-94) ---------------------------
+struct SnPotOffset { short dx, dy, dz, pad; double w; };   // w = 1/d^3
+
+__global__ void __launch_bounds__(128) sn_potential_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnPotOffset *__restrict__ off,
+                                                           int noff, double *__restrict__ V)
+{
+    const long long n = (long long)G.X * G.Y * G.nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x, y, z; sn_site_of(G, i, x, y, z);
+    double pot = 0.0;
+    for (int o = 0; o < noff; o++) {
+        const SnPotOffset f = off[o];
+        int xx = (x + f.dx) % G.X, yy = (y + f.dy) % G.Y, zz = (z + f.dz) % G.nz;
+        if (xx < 0) xx += G.X;
+        if (yy < 0) yy += G.Y;
+        if (zz < 0) zz += G.nz;
+        const float4 c = lat[sn_pidx(G, xx, yy, zz)];
+        pot += (double)c.w * ((double)c.x * f.dx + (double)c.y * f.dy + (double)c.z * f.dz) * f.w;
+    }
+    V[i] = pot;
+}
