@@ -1,0 +1,71 @@
+"""GPU parity tests for the observables of starrynight-analysis.c, through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import oracle_api as oa
+from tests.helpers import CASE_NAMES, load_case, sim_for
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sn(built):
+    import starrynight_b200
+    return starrynight_b200
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_observables_against_golden(sn, name):
+    g, p = load_case(name)
+    lat = g["lattice"]
+    n = p.X * p.Y * p.Z
+    with sim_for(sn, p, lat) as sim:
+        P = sim.polarisation()
+        assert P[0] == pytest.approx(float(g["polarisation_f64"]), rel=1e-12, abs=1e-15)       # analysis.c:48-62
+        assert np.allclose(P, lat[..., :3].astype(np.float64).reshape(-1, 3).sum(0) / n, rtol=1e-12, atol=1e-15)
+        assert sim.landau_order() == pytest.approx(float(g["landau_f64"]), rel=1e-12)           # analysis.c:506-526
+        assert sim.landau_order() == pytest.approx(float(g["landau_f32"]), rel=2e-5)            # float accumulators there
+        if "potential_f64" in g:
+            V = sim.dipole_potential().ravel()                                                   # analysis.c:65-94
+            ref = g["potential_f64"]
+            assert np.max(np.abs(V - ref)) < 1e-12 * np.max(np.abs(ref)) * 50
+            assert np.max(np.abs(V - g["potential_f32"])) < 2e-5 * np.max(np.abs(ref))
+        if "rdf_f64" in g:
+            fe, afe, cnt = sim.radial_order_parameter()                                          # analysis.c:528-598
+            ofe, oafe, ocnt = oa.Oracle("f64").rdf(p, lat)
+            assert np.array_equal(cnt, ocnt.astype(np.int64))
+            assert np.allclose(fe, ofe, rtol=1e-11, atol=1e-9)
+            assert np.allclose(afe, oafe, rtol=1e-11, atol=1e-9)
+            rows = g["rdf_f64"]                     # what the reference printed: r2 r FE AFE count T
+            nz = np.nonzero(cnt)[0]
+            assert np.array_equal(rows[:, 0].astype(int), nz)
+            assert np.allclose(rows[:, 2], fe[nz] / cnt[nz], atol=6e-7)
+            assert np.allclose(rows[:, 3], afe[nz] / cnt[nz], atol=6e-7)
+
+
+def test_flat_lattice_potential_counts_the_plane_13_times(sn):
+    """dipole_potential always loops dz in [-6,6]; on Z == 1 every dz lands on the same plane
+    through %Z (analysis.c:73-91).  The kernel keeps that behaviour."""
+    p = oa.make_params(14, 12, 1, 3, 1.0, 0.0, (0, 0, 0), 1.0)
+    lat = oa.random_lattice(14, 12, 1, seed=8)
+    with sim_for(sn, p, lat) as sim:
+        V = sim.dipole_potential().ravel()
+    ref = oa.Oracle("f64").potential_map(p, lat)
+    assert np.max(np.abs(V - ref)) < 1e-11
+
+
+def test_large_lattice_properties(sn):
+    """Size-independent properties at a size the CPU oracle cannot finish: ferroelectric state."""
+    X = 96
+    lat = np.zeros((X, X, X, 4), np.float32)
+    lat[..., 0] = 1.0
+    lat[..., 3] = 1.0
+    with sn.Simulation(X, X, X, CageStrain=1.0, K=0.0) as sim:
+        sim.set_lattice(lat)
+        assert np.allclose(sim.polarisation(), [1.0, 0.0, 0.0])
+        fe, afe, cnt = sim.radial_order_parameter()
+        nz = cnt > 0
+        assert np.array_equal(fe[nz], cnt[nz].astype(np.float64))        # FE correlation exactly 1 at every r
+        assert cnt[1] == 6 * X ** 3 and cnt[74] == 120 * X ** 3          # int64 counts: beyond int32 at 512^3
+        e = sim.total_energy(sn.SN_PREC_F64)
+        assert e[1] == pytest.approx(-3.0 * X ** 3, rel=1e-13)

@@ -1,0 +1,188 @@
+"""GPU tests of the Metropolis sweep (MC_moves / MC_move, montecarlo-core.c:143-191).
+
+The colour-sweep order and the Philox stream necessarily give a different Markov
+chain from the reference's serial random-site MT19937 chain, so parity is
+(i) structural invariants, (ii) exactness of the energies the chain is built on
+(test_gpu_energy.py), and (iii) agreement of equilibrium observables with the
+reference chain (the CPU oracle, bit-equal to the reference) within statistical
+error bars from independent seeds."""
+import numpy as np
+import pytest
+
+from oracle import oracle_api as oa
+from tests.helpers import sim_for
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sn(built):
+    import starrynight_b200
+    return starrynight_b200
+
+
+KERNELS = ["colour", "auto"]
+
+
+def kernel_id(sn, k):
+    return {"colour": sn.SN_KERNEL_COLOUR, "auto": sn.SN_KERNEL_AUTO}[k]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("shape", [(32, 32, 32), (20, 20, 28), (13, 17, 11), (24, 24, 1), (64, 32, 32)])
+def test_sweep_invariants(sn, shape, kernel):
+    X, Y, Z = shape
+    lat = oa.random_lattice(X, Y, Z, seed=5, lengths=(1.0, 0.5, 0.0), prevalence=(0.6, 0.3, 0.1))
+    p = oa.make_params(X, Y, Z, 3, 1.0, 0.0, (0.02, 0, 0), 1.0)
+    with sim_for(sn, p, lat, kernel=kernel_id(sn, kernel)) as sim:
+        sim.MC_sweeps(3)
+        acc, rej, vac = sim.counters()
+        out = sim.get_lattice()
+    n = X * Y * Z
+    nvac = int((lat[..., 3] == 0).sum())
+    assert vac == 3 * nvac                          # vacancies are skipped, never counted (montecarlo-core.c:163)
+    assert acc + rej == 3 * (n - nvac)
+    assert 0.05 < acc / (acc + rej) < 0.95
+    assert np.array_equal(out[..., 3], lat[..., 3])                    # length / species never changes (:173,:184)
+    assert np.array_equal(out[lat[..., 3] == 0], lat[lat[..., 3] == 0])
+    live = lat[..., 3] != 0
+    assert np.max(np.abs(np.linalg.norm(out[..., :3][live], axis=-1) - 1.0)) < 2e-6
+    assert (out[..., :3][live] != lat[..., :3][live]).any(axis=-1).mean() > 0.3
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_sweep_is_deterministic_and_seed_dependent(sn, kernel):
+    lat = oa.random_lattice(32, 32, 32, seed=6)
+    outs = []
+    for seed in (1, 1, 2):
+        with sn.Simulation(32, 32, 32, seed=seed, kernel=kernel_id(sn, kernel)) as sim:
+            sim.set_lattice(lat)
+            sim.MC_sweeps(2)
+            sim.MC_sweeps(1)
+            outs.append(sim.get_lattice())
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_ghost_shell_stays_consistent(sn, kernel):
+    """After sweeps the energy computed through the ghost shell must equal the energy of the
+    downloaded lattice re-uploaded from scratch (ghosts rebuilt): every boundary update wrote its images."""
+    lat = oa.random_lattice(32, 32, 32, seed=7)
+    with sn.Simulation(32, 32, 32, CageStrain=1.0, kernel=kernel_id(sn, kernel)) as sim:
+        sim.set_lattice(lat)
+        sim.MC_sweeps(5)
+        e_live = sim.total_energy(sn.SN_PREC_F64)
+        out = sim.get_lattice()
+        sim.set_lattice(out)
+        e_fresh = sim.total_energy(sn.SN_PREC_F64)
+    assert np.array_equal(e_live, e_fresh)
+    p = oa.make_params(32, 32, 32, 3, 1.0, 0.0, (0, 0, 0), 1.0)
+    assert np.allclose(e_live, oa.Oracle("f64").total_energy(p, out), rtol=1e-11, atol=1e-8)
+
+
+def test_zero_temperature_only_goes_downhill(sn):
+    """T = 0 => beta = +inf: accept iff dE < 0 (main.c:215, montecarlo-core.c:179)."""
+    lat = oa.random_lattice(16, 16, 16, seed=8)
+    with sn.Simulation(16, 16, 16, CageStrain=1.0, beta=float("inf")) as sim:
+        sim.set_lattice(lat)
+        e = [sim.total_energy(sn.SN_PREC_F64).sum()]
+        for _ in range(6):
+            sim.MC_sweeps(1)
+            e.append(sim.total_energy(sn.SN_PREC_F64).sum())
+    assert all(b <= a + 1e-6 for a, b in zip(e, e[1:]))
+    assert e[-1] < e[0] - 100
+
+
+def test_constrain_to_x_proposals(sn):
+    """ConstrainToX: every accepted orientation is one of the six <100> vectors (config.c:230-263)."""
+    lat = oa.random_lattice(16, 16, 16, seed=9)
+    with sn.Simulation(16, 16, 16, ConstrainToX=True, beta=0.2) as sim:
+        sim.set_lattice(lat)
+        sim.MC_sweeps(30)
+        out = sim.get_lattice()[..., :3].reshape(-1, 3)
+    moved = (out != lat[..., :3].reshape(-1, 3)).any(1)
+    assert moved.mean() > 0.9
+    v = out[moved]
+    assert np.all(np.sort(np.abs(v), axis=1) == np.array([0, 0, 1], np.float32))
+    frac = [(np.argmax(np.abs(v), 1) == k).mean() for k in range(3)]
+    assert all(abs(f - 1 / 3) < 0.05 for f in frac)
+
+
+def test_dim2_proposals_stay_in_plane(sn):
+    lat = oa.random_lattice(16, 16, 16, seed=10)
+    with sn.Simulation(16, 16, 16, DIM=2, beta=0.2) as sim:
+        sim.set_lattice(lat)
+        sim.MC_sweeps(30)
+        out = sim.get_lattice()[..., :3].reshape(-1, 3)
+    moved = (out != lat[..., :3].reshape(-1, 3)).any(1)
+    assert np.all(out[moved][:, 2] == 0)
+
+
+def test_infinite_temperature_proposals_are_uniform_on_the_sphere(sn):
+    """beta = 0 accepts everything: the lattice becomes a sample of the proposal distribution."""
+    lat = oa.random_lattice(32, 32, 32, seed=11)
+    with sn.Simulation(32, 32, 32, beta=0.0) as sim:
+        sim.set_lattice(lat)
+        sim.MC_sweeps(1)
+        acc, rej, vac = sim.counters()
+        v = sim.get_lattice()[..., :3].reshape(-1, 3).astype(np.float64)
+    assert rej == 0 and acc == 32 ** 3
+    n = len(v)
+    assert np.all(np.abs(v.mean(0)) < 5 / np.sqrt(3 * n))                   # <p> = 0, var 1/3 per component
+    assert np.all(np.abs((v ** 2).mean(0) - 1 / 3) < 5 * np.sqrt(4 / 45 / n))
+    hist, _ = np.histogram(v[:, 2], bins=20, range=(-1, 1))                 # z uniform on [-1,1] (Archimedes)
+    assert np.all(np.abs(hist - n / 20) < 6 * np.sqrt(n / 20))
+
+
+def _reference_chain_stats(p, lat0, seeds, eqm, nsamp, stride):
+    """<E>/N, <P_x>, acceptance from the reference's serial chain (oracle f32, bit-equal to the reference)."""
+    o = oa.Oracle("f32")
+    n = p.X * p.Y * p.Z
+    rows = []
+    for s in seeds:
+        lat = np.ascontiguousarray(lat0, np.float32)
+        mt = o.mt(s)
+        o.mc_moves(p, lat, mt, eqm * n)
+        es, ps, acc, rej = [], [], 0, 0
+        for _ in range(nsamp):
+            a, r = o.mc_moves(p, lat, mt, stride * n)
+            acc += a; rej += r
+            es.append(o.total_energy(p, lat).sum() / n)
+            ps.append(o.polarisation(p, lat))
+        rows.append((np.mean(es), np.mean(ps), acc / (acc + rej)))
+    return np.array(rows)
+
+
+@pytest.mark.parametrize("T,Ex", [(150, 0.3), (300, 0.3), (600, 0.5)])
+def test_equilibrium_observables_match_reference_chain(sn, T, Ex):
+    """Energy per site, polarisation along an applied field and acceptance ratio at equilibrium:
+    colour-sweep Philox chain on the GPU vs the reference's serial chain, independent seeds on both
+    sides, agreement within 4.5 combined standard errors."""
+    X = 10
+    beta = 1.0 / (T / 300.0)
+    p = oa.make_params(X, X, X, 3, 1.0, 0.0, (float(np.float32(Ex)), 0.0, 0.0), beta)
+    lat0 = oa.random_lattice(X, X, X, seed=12)
+    eqm, nsamp, stride = 120, 20, 6
+    ref = _reference_chain_stats(p, lat0, seeds=range(100, 106), eqm=eqm, nsamp=nsamp, stride=stride)
+    R = 16
+    with sim_for(sn, p, nreplicas=R, seed=4242) as sim:
+        for r in range(R):
+            sim.set_lattice(lat0, r)
+        sim.MC_sweeps(eqm)
+        sim.reset_counters()
+        es, ps = np.zeros((R, nsamp)), np.zeros((R, nsamp))
+        for k in range(nsamp):
+            sim.MC_sweeps(stride)
+            for r in range(R):
+                es[r, k] = sim.total_energy(sn.SN_PREC_F32, r).sum() / X ** 3
+                ps[r, k] = sim.polarisation(r)[0]
+        ratios = []
+        for r in range(R):
+            a, rj, _ = sim.counters(r)
+            ratios.append(a / (a + rj))
+    gpu = np.stack([es.mean(1), ps.mean(1), np.array(ratios)], 1)
+    for col, what in enumerate(("energy per site", "polarisation", "acceptance ratio")):
+        m_ref, m_gpu = ref[:, col].mean(), gpu[:, col].mean()
+        se = np.sqrt(ref[:, col].var(ddof=1) / len(ref) + gpu[:, col].var(ddof=1) / len(gpu))
+        assert abs(m_ref - m_gpu) < 4.5 * se + 2e-4, f"T={T}: {what} reference {m_ref:.5f} vs GPU {m_gpu:.5f} (se {se:.5f})"
