@@ -28,17 +28,16 @@ struct SnSweepArgs {
     float4 *peer_lo, *peer_hi;      // Z-slab neighbours' padded lattices (replica 0 base) or null
 };
 
-// Write a site and every ghost image of it: periodic images in x, y (and z when
-// the handle owns the whole Z), and the neighbouring slabs' ghost planes.
-__device__ __forceinline__ void sn_store_site(float4 *__restrict__ lat, float4 *__restrict__ peer_lo,
-                                              float4 *__restrict__ peer_hi, const SnGeom &G,
-                                              int x, int y, int z, const float4 v)
+// Ghost images of a boundary site: periodic images in x, y (and z when the handle
+// owns the whole Z), and the neighbouring slabs' ghost planes.  Rare (surface
+// sites only), so kept out of line to keep the sweep kernels' hot code small.
+__device__ __noinline__ void sn_store_images(float4 *__restrict__ lat, float4 *__restrict__ peer_lo,
+                                             float4 *__restrict__ peer_hi, const SnGeom &G,
+                                             int x, int y, int z, const float4 v)
 {
-    lat[sn_pidx(G, x, y, z)] = v;
     const int g = G.g, gz = G.gz;
     const bool bx = x < g || x >= G.X - g, by = y < g || y >= G.Y - g;
     const bool bz = gz > 0 && (z < gz || z >= G.nz - gz);
-    if (!(bx || by || bz)) return;
     const int kx = bx ? (g + G.X - 1) / G.X : 0, ky = by ? (g + G.Y - 1) / G.Y : 0;
     const int kz = (bz && G.periodic_z) ? (gz + G.nz - 1) / G.nz : 0;
     for (int ix = -kx; ix <= kx; ix++) {
@@ -58,6 +57,18 @@ __device__ __forceinline__ void sn_store_site(float4 *__restrict__ lat, float4 *
             }
         }
     }
+}
+
+// Write a site and, if it lies within the ghost width of a face, every image of it.
+__device__ __forceinline__ void sn_store_site(float4 *__restrict__ lat, float4 *__restrict__ peer_lo,
+                                              float4 *__restrict__ peer_hi, const SnGeom &G,
+                                              int x, int y, int z, const float4 v)
+{
+    lat[sn_pidx(G, x, y, z)] = v;
+    const int g = G.g, gz = G.gz;
+    const bool bx = x < g || x >= G.X - g, by = y < g || y >= G.Y - g;
+    const bool bz = gz > 0 && (z < gz || z >= G.nz - gz);
+    if (bx || by || bz) sn_store_images(lat, peer_lo, peer_hi, G, x, y, z, v);
 }
 
 __device__ __forceinline__ void sn_count(unsigned long long *__restrict__ c, bool attempted, bool accepted, bool vacant)

@@ -16,20 +16,20 @@
 //     LDS.128 without bank conflicts -- and every neighbour address is
 //     base + compile-time immediate.
 //   * Inside a tile the 64 site colours are visited as 16 super-passes (cx,cy).
-//     A thread owns a segment of 4 consecutive z sites of one (x,y) column, i.e.
-//     the four colours (cx,cy,0..3).  None of the 28 neighbour columns around it
-//     changes during the super-pass (they belong to other (cx,cy) classes), so
-//     their contribution to the local fields of all 4 sites is gathered in one
-//     go with a sliding z window: 8 loads serve 4 x 5 neighbours (2.2x fewer
-//     shared-memory reads than 4 independent gathers), all 798 tensor FFMAs per
-//     attempt are still executed.  Only the centre column changes: the 4 sites are
-//     then decided in sequence, the field of the later ones corrected in registers
-//     for the earlier accepted moves (own thread, and the segment above via
-//     shuffle).  Every attempt is a full fresh dE over the cut-off sphere.
-//   * Warp specialisation: warps 0-1 gather half of the neighbour columns (and
-//     the centre column) and run the sequential chain; warps 2-3 gather the other
-//     half, hand their partial fields over through shared memory, and meanwhile
-//     draw the Philox proposals for the next super-pass.
+//     Two lanes own a segment of 4 consecutive z sites of one (x,y) column, i.e.
+//     the four colours (cx,cy,0..3), 2 sites each.  None of the 28 neighbour
+//     columns around it changes during the super-pass (they belong to other
+//     (cx,cy) classes), so their contribution to the local fields is gathered
+//     once with a sliding z window (one load serves both sites).  Only the centre
+//     column changes: the 4 sites are then decided in sequence, the fields of the
+//     later ones corrected in registers for the earlier accepted moves (partner
+//     lane and the segment above via shuffles).  Every attempt is a full fresh dE
+//     over the cut-off sphere.
+//   * All 128 threads run one ~22 KB instruction stream (it has to stay inside the
+//     instruction cache: a first version with two 30 KB warp roles spent half its
+//     cycles waiting for instructions).  A thread gathers the fields of 2 sites;
+//     neighbours r and -r share the tensor T(r) = T(-r), so their moments are added
+//     first and the tensor applied once (582 instead of 798 FP ops per attempt).
 //   * Accepted moves are written to the shared tile and straight to global
 //     memory together with their ghost images (periodic faces, and the
 //     neighbouring GPU's ghost planes over NVLink for a Z-slab handle).
@@ -48,10 +48,7 @@ constexpr int NQ = 7;                    // z samples per residue box (window of
 constexpr int BOX_F4 = BX * BX * NQ;     // float4 per residue box
 constexpr int BOX_BYTES = BOX_F4 * 16;   // 54208 bytes moved by each TMA
 constexpr int BOX_STRIDE_F4 = 3392;      // 54272 B: box pitch rounded up to 128 B (TMA destination alignment)
-constexpr int SEGS = 64;                 // segments (threads of one warp group) per super-pass
-constexpr int OFF_XF = 4 * BOX_STRIDE_F4 * 16;             // partial fields: float4[6][64]
-constexpr int OFF_XP = OFF_XF + 6 * SEGS * 16;             // proposals: float4[2][4][64]
-constexpr int OFF_BAR = OFF_XP + 2 * 4 * SEGS * 16;        // mbarrier
+constexpr int OFF_BAR = 4 * BOX_STRIDE_F4 * 16;            // mbarrier
 constexpr int SMEM_BYTES = OFF_BAR + 16;
 constexpr int THREADS = 128;
 
@@ -70,37 +67,69 @@ __device__ __forceinline__ void sn_mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
-// Gather the contribution of this warp group's neighbour columns to the local
-// fields of the 4 sites of a segment.  `tile` = shared float4 array, B = float4
-// index of (column lx,ly; q = k+1) in residue box 0.
-template <int GROUP, bool SPECIES>
-__device__ __forceinline__ void sn_tile_gather(const float4 *__restrict__ tile, const int B, float3 (&F)[4], float3 (&G)[4],
-                                               float4 (&old)[4])
+// One neighbour pair r = (DX,DY,DZ) and -r: T(r) = T(-r), so the two moments are
+// added first and the tensor applied once (12 instead of 18 FP ops for a full tensor).
+template <int DX, int DY, int DZ, bool SPECIES>
+__device__ __forceinline__ void sn_accumulate_pair(float3 &F, float3 &G, const float4 a, const float4 b)
+{
+    constexpr float txx = sn_T(DX, DY, DZ, 0, 0), tyy = sn_T(DX, DY, DZ, 1, 1), tzz = sn_T(DX, DY, DZ, 2, 2);
+    constexpr float txy = sn_T(DX, DY, DZ, 0, 1), txz = sn_T(DX, DY, DZ, 0, 2), tyz = sn_T(DX, DY, DZ, 1, 2);
+    float ax, ay, az;
+    if constexpr (SPECIES) { ax = fmaf(a.x, a.w, b.x * b.w); ay = fmaf(a.y, a.w, b.y * b.w); az = fmaf(a.z, a.w, b.z * b.w); }
+    else { ax = a.x + b.x; ay = a.y + b.y; az = a.z + b.z; }
+    F.x = fmaf(txx, ax, F.x);
+    F.y = fmaf(tyy, ay, F.y);
+    F.z = fmaf(tzz, az, F.z);
+    if constexpr (txy != 0.0f) { F.x = fmaf(txy, ay, F.x); F.y = fmaf(txy, ax, F.y); }
+    if constexpr (txz != 0.0f) { F.x = fmaf(txz, az, F.x); F.z = fmaf(txz, ax, F.z); }
+    if constexpr (tyz != 0.0f) { F.y = fmaf(tyz, az, F.y); F.z = fmaf(tyz, ay, F.z); }
+    if constexpr (DX * DX + DY * DY + DZ * DZ == 1) {
+        if constexpr (SPECIES) { G.x += a.x + b.x; G.y += a.y + b.y; G.z += a.z + b.z; }
+        else { G.x += ax; G.y += ay; G.z += az; }
+    }
+}
+
+// Local fields of the thread's 2 consecutive z sites from all 29 columns.  pe[e+3]
+// points at the thread's own column, plane (first site + e); a neighbour column is
+// a compile-time immediate away.  Each column pair (+c, -c) is loaded once for
+// both sites (sliding z window) and combined with the pair symmetry.
+template <bool SPECIES>
+__device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], float3 (&F)[2], float3 (&G)[2], float4 (&old)[2])
 {
     sn_static_for<-3, 4>([&](auto dxc) {
         sn_static_for<-3, 4>([&](auto dyc) {
             constexpr int DX = decltype(dxc)::value, DY = decltype(dyc)::value;
             constexpr int r2xy = DX * DX + DY * DY;
-            if constexpr (r2xy <= 9) {
-                constexpr bool centre = (DX == 0 && DY == 0);
-                constexpr bool upper = DX > 0 || (DX == 0 && DY > 0);
-                constexpr bool mine = centre ? GROUP == 0 : (upper ? GROUP == 0 : GROUP == 1);
-                if constexpr (mine) {
-                    constexpr int M = snt::half_height(r2xy);
-                    sn_static_for<-M, 4 + M>([&](auto ec) {
-                        constexpr int E = decltype(ec)::value;
-                        const float4 w = tile[snt::residue(E) * snt::BOX_STRIDE_F4 + B + (DX * snt::BX + DY) * snt::NQ + snt::qshift(E)];
-                        if constexpr (centre && E >= 0 && E <= 3) old[E] = w;
-                        sn_static_for<0, 4>([&](auto sc) {
-                            constexpr int S = decltype(sc)::value, DZ = E - S;
-                            if constexpr (DZ * DZ <= 9 - r2xy && !(centre && DZ == 0))
-                                sn_accumulate<DX, DY, DZ, SPECIES>(F[S], G[S], w);
-                        });
+            constexpr bool upper = DX > 0 || (DX == 0 && DY > 0);
+            if constexpr (r2xy <= 9 && upper) {
+                constexpr int M = snt::half_height(r2xy);
+                constexpr int C = (DX * snt::BX + DY) * snt::NQ;
+                float4 wp[2 * M + 2], wm[2 * M + 2];
+                sn_static_for<-M, 2 + M>([&](auto ec) {
+                    constexpr int E = decltype(ec)::value;
+                    wp[E + M] = pe[E + 3][C];
+                    wm[E + M] = pe[E + 3][-C];
+                });
+                sn_static_for<0, 2>([&](auto sc) {
+                    sn_static_for<-M, M + 1>([&](auto dzc) {
+                        constexpr int S = decltype(sc)::value, DZ = decltype(dzc)::value;
+                        sn_accumulate_pair<DX, DY, DZ, SPECIES>(F[S], G[S], wp[S + DZ + M], wm[S - DZ + M]);
                     });
-                }
+                });
             }
         });
     });
+    {   // own column: pairs (0,0,+-dz); also yields the current values of the 2 sites
+        float4 w[8];
+        sn_static_for<0, 8>([&](auto ec) { constexpr int E = decltype(ec)::value; w[E] = pe[E][0]; });
+        old[0] = w[3]; old[1] = w[4];
+        sn_static_for<0, 2>([&](auto sc) {
+            sn_static_for<1, 4>([&](auto dzc) {
+                constexpr int S = decltype(sc)::value, DZ = decltype(dzc)::value;
+                sn_accumulate_pair<0, 0, DZ, SPECIES>(F[S], G[S], w[3 + S + DZ], w[3 + S - DZ]);
+            });
+        });
+    }
 }
 
 struct SnTilePhase {
@@ -115,14 +144,12 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float4 *tile = reinterpret_cast<float4 *>(smem);
-    float4 *xF = reinterpret_cast<float4 *>(smem + snt::OFF_XF);
-    float4 *xP = reinterpret_cast<float4 *>(smem + snt::OFF_XP);
     const uint32_t bar = sn_smem_u32(smem + snt::OFF_BAR);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int group = warp >> 1;                         // 0: gather + chain, 1: gather + proposals
-    const int k = lane & 3, j = (lane >> 2) & 3, i = ((warp & 1) << 1) | (lane >> 4);
-    const int seg = ((warp & 1) << 5) | lane;            // 0..63 inside the group
+    // thread -> (column i,j ; segment k of 4 z sites ; half h of the segment).  k and the low bit of j
+    // vary inside a quarter-warp, so its 8 lanes read 8 distinct 16-byte bank groups (28 j + k mod 8).
+    const int tid = threadIdx.x, lane = tid & 31, i = tid >> 5;
+    const int k = lane & 3, h = (lane >> 3) & 1, j = ((lane >> 2) & 1) | ((lane >> 4) << 1);
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -133,6 +160,14 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     const long long ntiles = (long long)ph.hx * ph.hy * ph.hz * ph.nrep;
     uint32_t parity = 0;
     const SnGeom &G = a.G;
+
+    // z part of the shared-memory index for plane (4k + 2h + e), e = -3..4
+    int zoff[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int w = 4 + 4 * k + 2 * h + (e - 3);          // plane index inside the 28-plane window
+        zoff[e] = (w & 3) * snt::BOX_STRIDE_F4 + (w >> 2);
+    }
 
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int iz = (int)(t % ph.hz), iy = (int)((t / ph.hz) % ph.hy), ix = (int)((t / ((long long)ph.hz * ph.hy)) % ph.hx);
@@ -160,129 +195,108 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         float4 *plo = a.peer_lo ? a.peer_lo + (long long)rep * G.rep_stride : nullptr;
         float4 *phi = a.peer_hi ? a.peer_hi + (long long)rep * G.rep_stride : nullptr;
 
-        // trial orientations + accept uniforms for the 4 sites of this thread's segment in super-pass sp
-        auto draw = [&](int sp) {
-            const int cx = sp >> 2, cy = sp & 3;
-            const int x = x0 + cx + 4 * i, y = y0 + cy + 4 * j;
-            float4 *dst = xP + (sp & 1) * 4 * snt::SEGS + seg;
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                const int z = z0 + 4 * k + s;
-                const unsigned long long gsite = ((unsigned long long)x * G.Y + y) * G.Z + (G.z0 + z);
-                const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ ((uint32_t)rep << 8),
-                                                   a.sweep_lo, a.sweep_hi, a.key0, a.key1);
-                const float3 np = sn_propose(tm, sn_u01(r.x), sn_u01(r.y));
-                dst[s * snt::SEGS] = make_float4(np.x, np.y, np.z, sn_u01(r.z));
-            }
-        };
-        if (group == 1) draw(0);                        // overlaps the TMA flight
-
         sn_mbar_wait(bar, parity);
         parity ^= 1;
-        __syncthreads();
 
         int n_acc = 0, n_rej = 0, n_vac = 0;
 #pragma unroll 1
         for (int sp = 0; sp < 16; sp++) {
             const int cx = sp >> 2, cy = sp & 3;
-            const int lx = snt::H + cx + 4 * i, ly = snt::H + cy + 4 * j;
-            const int B = (lx * snt::BX + ly) * snt::NQ + k + 1;
-            float3 F[4], Gc[4];
-            float4 old[4];
+            const int gx = x0 + cx + 4 * i, gy = y0 + cy + 4 * j, gz = z0 + 4 * k + 2 * h;
+            const int colbase = ((snt::H + cx + 4 * i) * snt::BX + (snt::H + cy + 4 * j)) * snt::NQ;
+            const float4 *pe[8];
 #pragma unroll
-            for (int s = 0; s < 4; s++) { F[s] = make_float3(0.f, 0.f, 0.f); Gc[s] = make_float3(0.f, 0.f, 0.f); old[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            for (int e = 0; e < 8; e++) pe[e] = tile + colbase + zoff[e];
 
-            if (group == 0) {
-                sn_tile_gather<0, SPECIES>(tile, B, F, Gc, old);
-            } else {
-                sn_tile_gather<1, SPECIES>(tile, B, F, Gc, old);
-                xF[0 * snt::SEGS + seg] = make_float4(F[0].x, F[0].y, F[0].z, F[1].x);
-                xF[1 * snt::SEGS + seg] = make_float4(F[1].y, F[1].z, F[2].x, F[2].y);
-                xF[2 * snt::SEGS + seg] = make_float4(F[2].z, F[3].x, F[3].y, F[3].z);
-                xF[3 * snt::SEGS + seg] = make_float4(Gc[0].x, Gc[0].y, Gc[0].z, Gc[1].x);
-                xF[4 * snt::SEGS + seg] = make_float4(Gc[1].y, Gc[1].z, Gc[2].x, Gc[2].y);
-                xF[5 * snt::SEGS + seg] = make_float4(Gc[2].z, Gc[3].x, Gc[3].y, Gc[3].z);
+            // trial orientations for the 2 sites (Philox keyed by global site, replica, sweep)
+            float3 np[2]; float ua[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const unsigned long long gsite = ((unsigned long long)gx * G.Y + gy) * G.Z + (G.z0 + gz + s);
+                const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ ((uint32_t)rep << 8),
+                                                   a.sweep_lo, a.sweep_hi, a.key0, a.key1);
+                np[s] = sn_propose(tm, sn_u01(r.x), sn_u01(r.y));
+                ua[s] = sn_u01(r.z);
             }
-            __syncthreads();
 
-            if (group == 0) {
-                {   // add the other group's partial fields
-                    const float4 v0 = xF[0 * snt::SEGS + seg], v1 = xF[1 * snt::SEGS + seg], v2 = xF[2 * snt::SEGS + seg];
-                    const float4 v3 = xF[3 * snt::SEGS + seg], v4 = xF[4 * snt::SEGS + seg], v5 = xF[5 * snt::SEGS + seg];
-                    F[0].x += v0.x; F[0].y += v0.y; F[0].z += v0.z; F[1].x += v0.w;
-                    F[1].y += v1.x; F[1].z += v1.y; F[2].x += v1.z; F[2].y += v1.w;
-                    F[2].z += v2.x; F[3].x += v2.y; F[3].y += v2.z; F[3].z += v2.w;
-                    Gc[0].x += v3.x; Gc[0].y += v3.y; Gc[0].z += v3.z; Gc[1].x += v3.w;
-                    Gc[1].y += v4.x; Gc[1].z += v4.y; Gc[2].x += v4.z; Gc[2].y += v4.w;
-                    Gc[2].z += v5.x; Gc[3].x += v5.y; Gc[3].y += v5.z; Gc[3].z += v5.w;
+            float3 F[2], Gc[2];
+            float4 old[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++) { F[s] = make_float3(0.f, 0.f, 0.f); Gc[s] = make_float3(0.f, 0.f, 0.f); }
+            sn_tile_gather2<SPECIES>(pe, F, Gc, old);
+
+            // The 4 sites of a segment interact: decide them in z order.  Step t belongs to the lane with
+            // h == t/2 (local site t&1); its accepted change is broadcast to the partner lane (lane^8) and to
+            // the segment below (lane-1 reads lane's value as "the segment above"), and folded into the
+            // fields of the later sites: T(0,0,dz) = diag(1,1,-2)/|dz|^3, cage term for |dz| = 1.
+            float3 dmS[4], dpS[4], dmU[4], dpU[4];
+            bool accepted[2] = {false, false};
+#pragma unroll
+            for (int t4 = 0; t4 < 4; t4++) {
+                const int s = t4 & 1;
+                float3 Fs = F[s], Gs = Gc[s];
+#pragma unroll
+                for (int t2 = 0; t2 < t4; t2++) {                 // earlier sites of this segment, dz = t2 - t4
+                    const int d = t4 - t2;
+                    const float w3 = d == 1 ? 1.0f : d == 2 ? 0.125f : (1.0f / 27.0f);
+                    Fs.x = fmaf(w3, dmS[t2].x, Fs.x); Fs.y = fmaf(w3, dmS[t2].y, Fs.y); Fs.z = fmaf(-2.0f * w3, dmS[t2].z, Fs.z);
+                    if (d == 1) { Gs.x += dpS[t2].x; Gs.y += dpS[t2].y; Gs.z += dpS[t2].z; }
                 }
-                const float4 *prop = xP + (sp & 1) * 4 * snt::SEGS + seg;
-                float3 dp[4], dm[4], dmu[4], dpu0 = make_float3(0.f, 0.f, 0.f);
-                const int gx = x0 + cx + 4 * i, gy = y0 + cy + 4 * j;
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    float3 Fs = F[s], Gs = Gc[s];
-                    // earlier sites of this segment, dz = s2 - s in {-1,-2,-3}: T(0,0,dz) = diag(1,1,-2)/|dz|^3
-#pragma unroll
-                    for (int s2 = 0; s2 < s; s2++) {
-                        const int d = s - s2;
-                        const float w3 = d == 1 ? 1.0f : d == 2 ? 0.125f : (1.0f / 27.0f);
-                        Fs.x = fmaf(w3, dm[s2].x, Fs.x); Fs.y = fmaf(w3, dm[s2].y, Fs.y); Fs.z = fmaf(-2.0f * w3, dm[s2].z, Fs.z);
-                        if (d == 1) { Gs.x += dp[s2].x; Gs.y += dp[s2].y; Gs.z += dp[s2].z; }
-                    }
-                    // earlier sites of the segment above (lane+1), dz = 4 + s2 - s in {1,2,3}
-#pragma unroll
-                    for (int s2 = 0; s2 < s; s2++) {
-                        const int d = 4 + s2 - s;
-                        const float w3 = d == 1 ? 1.0f : d == 2 ? 0.125f : (1.0f / 27.0f);
-                        Fs.x = fmaf(w3, dmu[s2].x, Fs.x); Fs.y = fmaf(w3, dmu[s2].y, Fs.y); Fs.z = fmaf(-2.0f * w3, dmu[s2].z, Fs.z);
-                        if (d == 1) { Gs.x += dpu0.x; Gs.y += dpu0.y; Gs.z += dpu0.z; }   // only s = 3, s2 = 0
-                    }
-                    const float4 o = old[s];
-                    const float4 pr = prop[s * snt::SEGS];
-                    const float3 np = make_float3(pr.x, pr.y, pr.z);
-                    const bool vacant = o.w == 0.0f;                                   // montecarlo-core.c:163
-                    const float dE = sn_delta_e(o, np, Fs, Gs, tm);
-                    const bool acc = !vacant && sn_accept(dE, tm.beta, pr.w);          // montecarlo-core.c:179
-                    dp[s] = acc ? make_float3(np.x - o.x, np.y - o.y, np.z - o.z) : make_float3(0.f, 0.f, 0.f);
-                    dm[s] = SPECIES ? make_float3(o.w * dp[s].x, o.w * dp[s].y, o.w * dp[s].z) : dp[s];
-                    if (s < 3) {
-                        dmu[s].x = __shfl_down_sync(0xffffffffu, dm[s].x, 1);
-                        dmu[s].y = __shfl_down_sync(0xffffffffu, dm[s].y, 1);
-                        dmu[s].z = __shfl_down_sync(0xffffffffu, dm[s].z, 1);
-                        if (k == 3) dmu[s] = make_float3(0.f, 0.f, 0.f);              // the segment above lies in the (static) halo
-                        if (SPECIES && s == 0) {
-                            dpu0.x = __shfl_down_sync(0xffffffffu, dp[0].x, 1);
-                            dpu0.y = __shfl_down_sync(0xffffffffu, dp[0].y, 1);
-                            dpu0.z = __shfl_down_sync(0xffffffffu, dp[0].z, 1);
-                            if (k == 3) dpu0 = make_float3(0.f, 0.f, 0.f);
-                        } else if (!SPECIES && s == 0) dpu0 = dmu[0];
-                    }
-                    if (acc) {
-                        const float4 nv = make_float4(np.x, np.y, np.z, o.w);
-                        tile[snt::residue(s) * snt::BOX_STRIDE_F4 + B + snt::qshift(s)] = nv;
-                        sn_store_site(glat, plo, phi, G, gx, gy, z0 + 4 * k + s, nv);
-                    }
-                    n_acc += acc; n_rej += (!acc && !vacant); n_vac += vacant;
+                for (int t2 = 0; t2 < t4; t2++) {                 // earlier sites of the segment above, dz = 4 + t2 - t4
+                    const int d = 4 + t2 - t4;
+                    const float w3 = d == 1 ? 1.0f : d == 2 ? 0.125f : (1.0f / 27.0f);
+                    Fs.x = fmaf(w3, dmU[t2].x, Fs.x); Fs.y = fmaf(w3, dmU[t2].y, Fs.y); Fs.z = fmaf(-2.0f * w3, dmU[t2].z, Fs.z);
+                    if (d == 1) { Gs.x += dpU[t2].x; Gs.y += dpU[t2].y; Gs.z += dpU[t2].z; }
                 }
-            } else if (sp < 15) {
-                draw(sp + 1);
+                const float4 o = old[s];
+                const bool mine = h == (t4 >> 1);
+                const bool vacant = o.w == 0.0f;                                            // montecarlo-core.c:163
+                const float dE = sn_delta_e(o, np[s], Fs, Gs, tm);
+                const bool acc = mine && !vacant && sn_accept(dE, tm.beta, ua[s]);          // montecarlo-core.c:179
+                float3 dp = acc ? make_float3(np[s].x - o.x, np[s].y - o.y, np[s].z - o.z) : make_float3(0.f, 0.f, 0.f);
+                if (acc) *const_cast<float4 *>(pe[3 + s]) = make_float4(np[s].x, np[s].y, np[s].z, o.w);
+                if (mine) accepted[s] = acc;
+                n_acc += acc; n_rej += (mine && !acc && !vacant); n_vac += (mine && vacant);
+                if (t4 < 3) {
+                    const int src = (lane & 23) | ((t4 >> 1) << 3);                        // the lane that owns step t4
+                    dpS[t4].x = __shfl_sync(0xffffffffu, dp.x, src);
+                    dpS[t4].y = __shfl_sync(0xffffffffu, dp.y, src);
+                    dpS[t4].z = __shfl_sync(0xffffffffu, dp.z, src);
+                    if constexpr (SPECIES) {
+                        const float ow = __shfl_sync(0xffffffffu, o.w, src);
+                        dmS[t4] = make_float3(ow * dpS[t4].x, ow * dpS[t4].y, ow * dpS[t4].z);
+                    } else dmS[t4] = dpS[t4];
+                    dpU[t4].x = __shfl_down_sync(0xffffffffu, dpS[t4].x, 1);
+                    dpU[t4].y = __shfl_down_sync(0xffffffffu, dpS[t4].y, 1);
+                    dpU[t4].z = __shfl_down_sync(0xffffffffu, dpS[t4].z, 1);
+                    if constexpr (SPECIES) {
+                        dmU[t4].x = __shfl_down_sync(0xffffffffu, dmS[t4].x, 1);
+                        dmU[t4].y = __shfl_down_sync(0xffffffffu, dmS[t4].y, 1);
+                        dmU[t4].z = __shfl_down_sync(0xffffffffu, dmS[t4].z, 1);
+                    } else dmU[t4] = dpU[t4];
+                    if (k == 3) { dpU[t4] = make_float3(0.f, 0.f, 0.f); dmU[t4] = make_float3(0.f, 0.f, 0.f); }   // above lies the static halo
+                }
             }
+            // accepted moves go straight to global memory (and to every ghost image / the neighbour GPU)
+#pragma unroll 1
+            for (int s = 0; s < 2; s++)
+                if (s == 0 ? accepted[0] : accepted[1])
+                    sn_store_site(glat, plo, phi, G, gx, gy, gz + s, make_float4(s == 0 ? np[0].x : np[1].x, s == 0 ? np[0].y : np[1].y,
+                                                                                 s == 0 ? np[0].z : np[1].z, s == 0 ? old[0].w : old[1].w));
             __syncthreads();
         }
-        if (group == 0) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
-                n_rej += __shfl_xor_sync(0xffffffffu, n_rej, o);
-                n_vac += __shfl_xor_sync(0xffffffffu, n_vac, o);
-            }
-            if (lane == 0) {
-                unsigned long long *c = a.counters + 3 * rep;
-                if (n_acc) atomicAdd(c + 0, (unsigned long long)n_acc);
-                if (n_rej) atomicAdd(c + 1, (unsigned long long)n_rej);
-                if (n_vac) atomicAdd(c + 2, (unsigned long long)n_vac);
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+            n_rej += __shfl_xor_sync(0xffffffffu, n_rej, o);
+            n_vac += __shfl_xor_sync(0xffffffffu, n_vac, o);
+        }
+        if (lane == 0) {
+            unsigned long long *c = a.counters + 3 * rep;
+            if (n_acc) atomicAdd(c + 0, (unsigned long long)n_acc);
+            if (n_rej) atomicAdd(c + 1, (unsigned long long)n_rej);
+            if (n_vac) atomicAdd(c + 2, (unsigned long long)n_vac);
         }
     }
 }
