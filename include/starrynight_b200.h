@@ -150,6 +150,10 @@ SN_API int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum, lo
 /* replaces dipole_potential() over the lattice (analysis.c:65-94,264-308): V[X][Y][nz] */
 SN_API int sn_potential_map(sn_handle *h, int replica, double *V);
 
+/* measurement aid for bench.py: sustained FFMA throughput of `device` in TFLOP/s, the
+ * denominator of the FP32 CUDA-core roofline (MEASURED_PEAKS.json carries no FP32 figure) */
+SN_API int sn_bench_fp32_peak(int device, double *tflops);
+
 /* ---- Z-slab decomposition across GPUs (one handle per GPU) ------------------
  * A slab handle keeps `cutoff` ghost planes below and above its own planes.
  * sn_get_boundary / sn_set_ghost move them through host memory (bootstrap and

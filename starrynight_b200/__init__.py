@@ -30,7 +30,7 @@ EXPORTS = [
     "sn_set_lattice", "sn_get_lattice", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_mc_sweeps",
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_site_energy",
     "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_get_boundary",
-    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer",
+    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.sn_ipc_export.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.sn_ipc_attach.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     lib.sn_attach_peer.argtypes = [H, C.c_int, H]
+    lib.sn_bench_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -269,6 +270,12 @@ class Simulation:
         a = (C.c_ubyte * 64).from_buffer_copy(lattice_handle)
         b = (C.c_ubyte * 64).from_buffer_copy(flags_handle)
         _check(self.lib.sn_ipc_attach(self.h, side, a, b))
+
+    def fp32_peak_tflops(self):
+        """FFMA microbenchmark on this handle's device (roofline denominator for bench.py)."""
+        out = C.c_double(0)
+        _check(self.lib.sn_bench_fp32_peak(self.params.device, C.byref(out)))
+        return out.value
 
     def attach_peer(self, side, peer: "Simulation"):
         _check(self.lib.sn_attach_peer(self.h, side, peer.h))

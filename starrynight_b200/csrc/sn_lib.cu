@@ -567,4 +567,47 @@ extern "C" int sn_potential_map(sn_handle *h, int replica, double *V)
     return SN_OK;
 }
 
+// ---- FP32 roofline denominator ---------------------------------------------------
+__global__ void __launch_bounds__(256) sn_ffma_peak_kernel(float *out, int iters, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int sn_bench_fp32_peak(int device, double *tflops)
+{
+    if (!tflops) return sn_fail(SN_ERR_INVALID, "sn_bench_fp32_peak: null");
+    SN_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SN_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    float *out;
+    SN_CUDA_CHECK(cudaMalloc(&out, sizeof(float) * blocks * 256));
+    cudaEvent_t e0, e1;
+    SN_CUDA_CHECK(cudaEventCreate(&e0));
+    SN_CUDA_CHECK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        SN_CUDA_CHECK(cudaEventRecord(e0));
+        sn_ffma_peak_kernel<<<blocks, 256>>>(out, iters, 0.999f, 0.001f);
+        SN_CUDA_CHECK(cudaEventRecord(e1));
+        SN_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SN_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * 256;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return SN_OK;
+}
+
 #include "sn_slab.cuh"
