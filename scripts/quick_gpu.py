@@ -22,5 +22,5 @@ for (X, Y, Z, reps) in cases:
         ms, n = sim.MC_sweeps_timed(5)
         acc, rej, vac = sim.counters()
         e = sim.total_energy(sn.SN_PREC_F32).sum() / (X * Y * Z)
-        print(f"{X}x{Y}x{Z} x{reps} kernel={kern}: {ms/5:.3f} ms/sweep, {X*Y*Z*reps*5/ms*1e3:.3e} attempts/s, launches {n}, accept {acc/(acc+rej):.4f}, E/N {e:.5f}", flush=True)
+        print(f"{X}x{Y}x{Z} x{reps} kernel={kern}: {ms/5:.3f} ms/sweep, {X*Y*Z*reps*5/ms*1e3:.3e} attempts/s, launches {n}, accept {acc/max(1,acc+rej):.4f}, E/N {e:.5f}", flush=True)
         sim.close()

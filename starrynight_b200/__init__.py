@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstarrynight_b200.so")
+LIB_PATH = os.environ.get("SN_B200_LIB", os.path.join(_HERE, "libstarrynight_b200.so"))   # override: kernel experiments only
 
 SN_PREC_F32, SN_PREC_F64, SN_PREC_REPLICA = 0, 1, 2
 SN_KERNEL_AUTO, SN_KERNEL_COLOUR, SN_KERNEL_TILED = 0, 1, 2

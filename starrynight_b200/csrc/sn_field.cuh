@@ -32,14 +32,15 @@ __host__ __device__ constexpr double sn_inv_d3(int r2)
            r2 == 8 ? 0.04419417382415922028 : r2 == 9 ? 0.03703703703703703704 : 0.0;
 }
 
-// T_ab(r) = delta_ab / d^3 - 3 r_a r_b / d^5, rounded once to float
+// T_ab(r) = (delta_ab r^2 - 3 r_a r_b) / (r^2 d^3), rounded once to float.  The integer numerator
+// makes vanishing entries exactly zero (e.g. the diagonal of r = (1,1,1)), so they cost no FFMA.
 __host__ __device__ constexpr float sn_T(int dx, int dy, int dz, int a, int b)
 {
     const int r2 = dx * dx + dy * dy + dz * dz;
     const int ra = a == 0 ? dx : a == 1 ? dy : dz;
     const int rb = b == 0 ? dx : b == 1 ? dy : dz;
-    const double i3 = sn_inv_d3(r2);
-    return (float)((a == b ? i3 : 0.0) - 3.0 * ra * rb * i3 / r2);
+    const int num = (a == b ? r2 : 0) - 3 * ra * rb;
+    return num == 0 ? 0.0f : (float)((double)num * sn_inv_d3(r2) / r2);
 }
 
 // accumulate neighbour m = (p_j, l_j) at compile-time offset (DX,DY,DZ) into F (and G when |r|=1)
@@ -50,9 +51,9 @@ __device__ __forceinline__ void sn_accumulate(float3 &F, float3 &G, const float4
     constexpr float txy = sn_T(DX, DY, DZ, 0, 1), txz = sn_T(DX, DY, DZ, 0, 2), tyz = sn_T(DX, DY, DZ, 1, 2);
     float ax = m.x, ay = m.y, az = m.z;
     if constexpr (SPECIES) { ax *= m.w; ay *= m.w; az *= m.w; }     // moment l_j p_j (montecarlo-core.c:102)
-    F.x = fmaf(txx, ax, F.x);
-    F.y = fmaf(tyy, ay, F.y);
-    F.z = fmaf(tzz, az, F.z);
+    if constexpr (txx != 0.0f) F.x = fmaf(txx, ax, F.x);
+    if constexpr (tyy != 0.0f) F.y = fmaf(tyy, ay, F.y);
+    if constexpr (tzz != 0.0f) F.z = fmaf(tzz, az, F.z);
     if constexpr (txy != 0.0f) { F.x = fmaf(txy, ay, F.x); F.y = fmaf(txy, ax, F.y); }
     if constexpr (txz != 0.0f) { F.x = fmaf(txz, az, F.x); F.z = fmaf(txz, ax, F.z); }
     if constexpr (tyz != 0.0f) { F.y = fmaf(tyz, az, F.y); F.z = fmaf(tyz, ay, F.z); }
@@ -135,5 +136,5 @@ __device__ __forceinline__ float3 sn_propose(const SnTerms &t, float u, float v)
 // beta = +inf (T = 0) with dE == 0 gives NaN and rejects, as in the reference.
 __device__ __forceinline__ bool sn_accept(float dE, float beta, float u)
 {
-    return dE < 0.0f || __expf(-dE * beta) > u;
+    return (dE < 0.0f) | (__expf(-dE * beta) > u);      // no short-circuit: keeps the warp converged
 }

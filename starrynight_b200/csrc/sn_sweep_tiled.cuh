@@ -48,9 +48,19 @@ constexpr int NQ = 7;                    // z samples per residue box (window of
 constexpr int BOX_F4 = BX * BX * NQ;     // float4 per residue box
 constexpr int BOX_BYTES = BOX_F4 * 16;   // 54208 bytes moved by each TMA
 constexpr int BOX_STRIDE_F4 = 3392;      // 54272 B: box pitch rounded up to 128 B (TMA destination alignment)
-constexpr int OFF_BAR = 4 * BOX_STRIDE_F4 * 16;            // mbarrier
+constexpr int NCOL = 14;                  // neighbour column pairs {(dx,dy), (-dx,-dy)} inside the cut-off disc
+constexpr int SITE_THREADS = 128;        // threads of one role; each owns 2 sites per super-pass
+constexpr int OFF_XF = 4 * BOX_STRIDE_F4 * 16;                 // partial fields handed from role B to role A: float2[2 buffers][3][128]
+constexpr int OFF_XP = OFF_XF + 2 * 3 * SITE_THREADS * 8;      // proposals drawn by role B: float4[2 buffers][2 sites][128]
+constexpr int OFF_BAR = OFF_XP + 2 * 2 * SITE_THREADS * 16;    // mbarrier
 constexpr int SMEM_BYTES = OFF_BAR + 16;
-constexpr int THREADS = 128;
+constexpr int THREADS = 256;
+// Column pairs (snt::col numbering) gathered by role A.  Role B works one super-pass ahead of role A's
+// chain, so it may not read a column of the class A is updating: seen from the next class (cx,cy+1)
+// those are the columns (0,-1), (0,3), and (-1,-1) when cx advances, i.e. pairs 0, 2 and 6.  Pairs 0 and
+// 5 are the in-plane cage-strain neighbours, kept with A so that B hands over dipole fields only.
+constexpr unsigned MASK_A = (1u << 0) | (1u << 2) | (1u << 5) | (1u << 6);
+constexpr unsigned MASK_B = ((1u << NCOL) - 1u) & ~MASK_A;
 
 __host__ __device__ constexpr int half_height(int r2xy) { return 9 - r2xy >= 9 ? 3 : 9 - r2xy >= 4 ? 2 : 9 - r2xy >= 1 ? 1 : 0; }
 __host__ __device__ constexpr int residue(int e) { return ((e % 4) + 4) % 4; }
@@ -67,68 +77,141 @@ __device__ __forceinline__ void sn_mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
+// Field accumulators of one site, kept as 9 independent FFMA chains (one per tensor entry)
+// so that a single warp per scheduler still has enough independent work in flight.
+struct SnAcc {
+    float xx, xy, xz, yx, yy, yz, zx, zy, zz;   // F.x = xx + xy + xz, ...
+    float gx, gy, gz;                           // cage-strain sum
+};
+
 // One neighbour pair r = (DX,DY,DZ) and -r: T(r) = T(-r), so the two moments are
 // added first and the tensor applied once (12 instead of 18 FP ops for a full tensor).
 template <int DX, int DY, int DZ, bool SPECIES>
-__device__ __forceinline__ void sn_accumulate_pair(float3 &F, float3 &G, const float4 a, const float4 b)
+__device__ __forceinline__ void sn_accumulate_pair(SnAcc &A, const float4 a, const float4 b)
 {
     constexpr float txx = sn_T(DX, DY, DZ, 0, 0), tyy = sn_T(DX, DY, DZ, 1, 1), tzz = sn_T(DX, DY, DZ, 2, 2);
     constexpr float txy = sn_T(DX, DY, DZ, 0, 1), txz = sn_T(DX, DY, DZ, 0, 2), tyz = sn_T(DX, DY, DZ, 1, 2);
     float ax, ay, az;
     if constexpr (SPECIES) { ax = fmaf(a.x, a.w, b.x * b.w); ay = fmaf(a.y, a.w, b.y * b.w); az = fmaf(a.z, a.w, b.z * b.w); }
     else { ax = a.x + b.x; ay = a.y + b.y; az = a.z + b.z; }
-    F.x = fmaf(txx, ax, F.x);
-    F.y = fmaf(tyy, ay, F.y);
-    F.z = fmaf(tzz, az, F.z);
-    if constexpr (txy != 0.0f) { F.x = fmaf(txy, ay, F.x); F.y = fmaf(txy, ax, F.y); }
-    if constexpr (txz != 0.0f) { F.x = fmaf(txz, az, F.x); F.z = fmaf(txz, ax, F.z); }
-    if constexpr (tyz != 0.0f) { F.y = fmaf(tyz, az, F.y); F.z = fmaf(tyz, ay, F.z); }
+    if constexpr (txx != 0.0f) A.xx = fmaf(txx, ax, A.xx);
+    if constexpr (tyy != 0.0f) A.yy = fmaf(tyy, ay, A.yy);
+    if constexpr (tzz != 0.0f) A.zz = fmaf(tzz, az, A.zz);
+    if constexpr (txy != 0.0f) { A.xy = fmaf(txy, ay, A.xy); A.yx = fmaf(txy, ax, A.yx); }
+    if constexpr (txz != 0.0f) { A.xz = fmaf(txz, az, A.xz); A.zx = fmaf(txz, ax, A.zx); }
+    if constexpr (tyz != 0.0f) { A.yz = fmaf(tyz, az, A.yz); A.zy = fmaf(tyz, ay, A.zy); }
     if constexpr (DX * DX + DY * DY + DZ * DZ == 1) {
-        if constexpr (SPECIES) { G.x += a.x + b.x; G.y += a.y + b.y; G.z += a.z + b.z; }
-        else { G.x += ax; G.y += ay; G.z += az; }
+        if constexpr (SPECIES) { A.gx += a.x + b.x; A.gy += a.y + b.y; A.gz += a.z + b.z; }
+        else { A.gx += ax; A.gy += ay; A.gz += az; }
     }
 }
 
-// Local fields of the thread's 2 consecutive z sites from all 29 columns.  pe[e+3]
-// points at the thread's own column, plane (first site + e); a neighbour column is
-// a compile-time immediate away.  Each column pair (+c, -c) is loaded once for
-// both sites (sliding z window) and combined with the pair symmetry.
-template <bool SPECIES>
-__device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], float3 (&F)[2], float3 (&G)[2], float4 (&old)[2])
+namespace snt {
+// the 14 neighbour columns of the upper half plane (dx > 0, or dx == 0 and dy > 0); each stands
+// for the pair {(dx,dy), (-dx,-dy)}
+struct Col { int dx, dy; };
+__host__ __device__ constexpr Col col(int idx)
 {
-    sn_static_for<-3, 4>([&](auto dxc) {
-        sn_static_for<-3, 4>([&](auto dyc) {
-            constexpr int DX = decltype(dxc)::value, DY = decltype(dyc)::value;
-            constexpr int r2xy = DX * DX + DY * DY;
-            constexpr bool upper = DX > 0 || (DX == 0 && DY > 0);
-            if constexpr (r2xy <= 9 && upper) {
-                constexpr int M = snt::half_height(r2xy);
-                constexpr int C = (DX * snt::BX + DY) * snt::NQ;
-                float4 wp[2 * M + 2], wm[2 * M + 2];
-                sn_static_for<-M, 2 + M>([&](auto ec) {
-                    constexpr int E = decltype(ec)::value;
-                    wp[E + M] = pe[E + 3][C];
-                    wm[E + M] = pe[E + 3][-C];
-                });
-                sn_static_for<0, 2>([&](auto sc) {
-                    sn_static_for<-M, M + 1>([&](auto dzc) {
-                        constexpr int S = decltype(sc)::value, DZ = decltype(dzc)::value;
-                        sn_accumulate_pair<DX, DY, DZ, SPECIES>(F[S], G[S], wp[S + DZ + M], wm[S - DZ + M]);
-                    });
-                });
-            }
+    int n = 0;
+    for (int dx = 0; dx <= 3; dx++)
+        for (int dy = -3; dy <= 3; dy++) {
+            if (dx * dx + dy * dy > 9 || !(dx > 0 || dy > 0)) continue;
+            if (n == idx) return Col{dx, dy};
+            n++;
+        }
+    return Col{0, 0};
+}
+}  // namespace snt
+
+template <int IDX>
+__device__ __forceinline__ void sn_tile_load_pair(const float4 *const (&pe)[8], float4 (&wp)[6], float4 (&wm)[6])
+{
+    constexpr snt::Col c = snt::col(IDX);
+    constexpr int M = snt::half_height(c.dx * c.dx + c.dy * c.dy);
+    constexpr int C = (c.dx * snt::BX + c.dy) * snt::NQ;
+    sn_static_for<-M, 2 + M>([&](auto ec) {
+        constexpr int E = decltype(ec)::value;
+#ifdef SN_EXP_NOLOAD      // experiment: no shared-memory traffic, arithmetic only
+        wp[E + M] = make_float4(C * 0.001f, E * 0.01f, 0.5f, 1.0f);
+        wm[E + M] = make_float4(C * 0.002f, E * 0.02f, 0.25f, 1.0f);
+#else
+        wp[E + M] = pe[E + 3][C];
+        wm[E + M] = pe[E + 3][-C];
+#endif
+    });
+}
+
+template <int IDX, bool SPECIES>
+__device__ __forceinline__ void sn_tile_compute_pair(const float4 (&wp)[6], const float4 (&wm)[6], SnAcc (&A)[2])
+{
+    constexpr snt::Col c = snt::col(IDX);
+    constexpr int M = snt::half_height(c.dx * c.dx + c.dy * c.dy);
+    sn_static_for<0, 2>([&](auto sc) {
+        sn_static_for<-M, M + 1>([&](auto dzc) {
+            constexpr int S = decltype(sc)::value, DZ = decltype(dzc)::value;
+#ifdef SN_EXP_NOFP        // experiment: loads only, one add per loaded word
+            if constexpr (DZ == 0 || (S == 0 && DZ < 0) || (S == 1 && DZ > 0)) { A[S].xx += wp[S + DZ + M].x; A[S].yy += wm[S - DZ + M].y; }
+#else
+            sn_accumulate_pair<c.dx, c.dy, DZ, SPECIES>(A[S], wp[S + DZ + M], wm[S - DZ + M]);
+#endif
         });
     });
-    {   // own column: pairs (0,0,+-dz); also yields the current values of the 2 sites
-        float4 w[8];
-        sn_static_for<0, 8>([&](auto ec) { constexpr int E = decltype(ec)::value; w[E] = pe[E][0]; });
-        old[0] = w[3]; old[1] = w[4];
-        sn_static_for<0, 2>([&](auto sc) {
-            sn_static_for<1, 4>([&](auto dzc) {
-                constexpr int S = decltype(sc)::value, DZ = decltype(dzc)::value;
-                sn_accumulate_pair<0, 0, DZ, SPECIES>(F[S], G[S], w[3 + S + DZ], w[3 + S - DZ]);
-            });
-        });
+}
+
+namespace snt {
+// next column-pair index >= idx that is in MASK (NCOL if none)
+__host__ __device__ constexpr int next_in(unsigned mask, int idx)
+{
+    while (idx < NCOL && !((mask >> idx) & 1u)) idx++;
+    return idx;
+}
+}  // namespace snt
+
+template <unsigned MASK, int IDX, bool SPECIES>
+__device__ __forceinline__ void sn_tile_gather_chain(const float4 *const (&pe)[8], SnAcc (&A)[2], float4 (&c0)[6], float4 (&c1)[6])
+{
+    // c0/c1 hold pair IDX (already loaded); load the next pair of the mask, then do the arithmetic of this one
+    if constexpr (IDX < snt::NCOL) {
+        constexpr int NEXT = snt::next_in(MASK, IDX + 1);
+        float4 n0[6], n1[6];
+        if constexpr (NEXT < snt::NCOL) sn_tile_load_pair<NEXT>(pe, n0, n1);
+        sn_tile_compute_pair<IDX, SPECIES>(c0, c1, A);
+        if constexpr (NEXT < snt::NCOL) sn_tile_gather_chain<MASK, NEXT, SPECIES>(pe, A, n0, n1);
+    }
+}
+
+// Contribution of the column pairs in MASK -- and of the thread's own column when CENTRE -- to
+// the local fields of the thread's 2 consecutive z sites.  pe[e+3] points at the thread's own
+// column, plane (first site + e); a neighbour column is a compile-time immediate away.  Each
+// column pair (+c, -c) is loaded once for both sites (sliding z window) and combined with the
+// pair symmetry.  The loads of the next pair are issued before the arithmetic of the current one.
+template <unsigned MASK, bool CENTRE, bool SPECIES>
+__device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], float3 (&F)[2], float3 (&G)[2], float4 (&old)[2])
+{
+    SnAcc A[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) A[s] = SnAcc{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    constexpr int FIRST = snt::next_in(MASK, 0);
+    if constexpr (FIRST < snt::NCOL) {
+        float4 c0[6], c1[6];
+        sn_tile_load_pair<FIRST>(pe, c0, c1);
+        sn_tile_gather_chain<MASK, FIRST, SPECIES>(pe, A, c0, c1);
+    }
+    if constexpr (CENTRE) {
+        // own column: pairs (0,0,+-dz); also yields the current values of the 2 sites
+        const float4 w0 = pe[0][0], w1 = pe[1][0], w2 = pe[2][0], w3 = pe[3][0], w4 = pe[4][0], w5 = pe[5][0], w6 = pe[6][0], w7 = pe[7][0];
+        old[0] = w3; old[1] = w4;
+        sn_accumulate_pair<0, 0, 1, SPECIES>(A[0], w4, w2);
+        sn_accumulate_pair<0, 0, 2, SPECIES>(A[0], w5, w1);
+        sn_accumulate_pair<0, 0, 3, SPECIES>(A[0], w6, w0);
+        sn_accumulate_pair<0, 0, 1, SPECIES>(A[1], w5, w3);
+        sn_accumulate_pair<0, 0, 2, SPECIES>(A[1], w6, w2);
+        sn_accumulate_pair<0, 0, 3, SPECIES>(A[1], w7, w1);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        F[s] = make_float3(A[s].xx + A[s].xy + A[s].xz, A[s].yx + A[s].yy + A[s].yz, A[s].zx + A[s].zy + A[s].zz);
+        G[s] = make_float3(A[s].gx, A[s].gy, A[s].gz);
     }
 }
 
@@ -146,10 +229,17 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     float4 *tile = reinterpret_cast<float4 *>(smem);
     const uint32_t bar = sn_smem_u32(smem + snt::OFF_BAR);
 
+    // Two roles of 128 threads (4 warps) each -- one warp of each role per scheduler, so that one
+    // role's issue slots fill the other's latency gaps:
+    //   role A gathers column pairs [0, SPLIT) and the own column, then runs the sequential chain;
+    //   role B gathers the remaining pairs, hands its partial fields over through shared memory and
+    //          draws the Philox proposals of the next super-pass while A is in the chain.
     // thread -> (column i,j ; segment k of 4 z sites ; half h of the segment).  k and the low bit of j
     // vary inside a quarter-warp, so its 8 lanes read 8 distinct 16-byte bank groups (28 j + k mod 8).
-    const int tid = threadIdx.x, lane = tid & 31, i = tid >> 5;
+    const int tid = threadIdx.x, role = tid >> 7, tl = tid & 127, lane = tid & 31, i = tl >> 5;
     const int k = lane & 3, h = (lane >> 3) & 1, j = ((lane >> 2) & 1) | ((lane >> 4) << 1);
+    float2 *xF = reinterpret_cast<float2 *>(smem + snt::OFF_XF);
+    float4 *xP = reinterpret_cast<float4 *>(smem + snt::OFF_XP);
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -174,7 +264,11 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         const int rep = (int)(t / ((long long)ph.hz * ph.hy * ph.hx));
         const int x0 = (2 * ix + ph.px) * snt::T, y0 = (2 * iy + ph.py) * snt::T, z0 = (2 * iz + ph.pz) * snt::T;
 
+#ifdef SN_EXP_NOTMA
+        if (tid == 0 && t == blockIdx.x) {
+#else
         if (tid == 0) {
+#endif
             // shared memory was last touched through the generic proxy; order it before the async-proxy writes
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4 * snt::BOX_BYTES) : "memory");
@@ -194,109 +288,192 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         float4 *glat = a.lat + (long long)rep * G.rep_stride;
         float4 *plo = a.peer_lo ? a.peer_lo + (long long)rep * G.rep_stride : nullptr;
         float4 *phi = a.peer_hi ? a.peer_hi + (long long)rep * G.rep_stride : nullptr;
+        const bool face_tile = x0 == 0 || x0 + snt::T == G.X || y0 == 0 || y0 + snt::T == G.Y || z0 == 0 || z0 + snt::T == G.nz;
 
+        // Trial orientations for the thread's 2 sites in super-pass sp from ONE Philox4x32-10 call keyed by
+        // (global site of the first one, replica, sweep): per site 64 random bits = 24 (accept) + 20 + 20.
+        auto draw = [&](int sp) {
+            const int gx = x0 + (sp >> 2) + 4 * i, gy = y0 + (sp & 3) + 4 * j, gz = z0 + 4 * k + 2 * h;
+            const unsigned long long gsite = ((unsigned long long)gx * G.Y + gy) * G.Z + (G.z0 + gz);
+            const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ ((uint32_t)rep << 8),
+                                               a.sweep_lo, a.sweep_hi, a.key0, a.key1);
+            const uint32_t wa[2] = {r.x, r.z}, wb[2] = {r.y, r.w};
+            float4 *dst = xP + (sp & 1) * 2 * snt::SITE_THREADS + tl;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const float u = (float)(wb[s] >> 12) * (1.0f / 1048576.0f);
+                const float v = (float)(((wb[s] & 0xfffu) << 8) | (wa[s] & 0xffu)) * (1.0f / 1048576.0f);
+                const float3 np = sn_propose(tm, u, v);
+                dst[s * snt::SITE_THREADS] = make_float4(np.x, np.y, np.z, sn_u01(wa[s]));
+            }
+        };
+        if (role == 1) draw(0);                          // overlaps the TMA flight
+
+#ifdef SN_EXP_NOTMA
+        if (t == blockIdx.x) { sn_mbar_wait(bar, parity); parity ^= 1; }
+#else
         sn_mbar_wait(bar, parity);
         parity ^= 1;
+#endif
+
+        if (tid == 32 && t + gridDim.x < ntiles) {
+            // pull the next tile's boxes into L2 while this one is being swept
+            const long long t2 = t + gridDim.x;
+            const int jz = (int)(t2 % ph.hz), jy = (int)((t2 / ph.hz) % ph.hy), jx = (int)((t2 / ((long long)ph.hz * ph.hy)) % ph.hx);
+            const int rep2 = (int)(t2 / ((long long)ph.hz * ph.hy * ph.hx));
+            const int nx0 = (2 * jx + ph.px) * snt::T, ny0 = (2 * jy + ph.py) * snt::T, nz0 = (2 * jz + ph.pz) * snt::T;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+                             ::"l"(&tmap), "r"(0), "r"(nz0 - 1 + r), "r"(ny0), "r"(nx0), "r"(rep2) : "memory");
+        }
+
+        // role B's share of the fields of super-pass sp, left in xF[sp & 1]
+        auto gather_b = [&](int sp) {
+            const int colbase = ((snt::H + (sp >> 2) + 4 * i) * snt::BX + (snt::H + (sp & 3) + 4 * j)) * snt::NQ;
+            const float4 *pe[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) pe[e] = tile + colbase + zoff[e];
+            float3 F[2], Gc[2];
+            float4 old[2];
+#ifdef SN_EXP_NOGB
+            sn_tile_gather2<0u, false, SPECIES>(pe, F, Gc, old);
+#else
+            sn_tile_gather2<snt::MASK_B, false, SPECIES>(pe, F, Gc, old);
+#endif
+            float2 *dst = xF + (sp & 1) * 3 * snt::SITE_THREADS + tl;
+            dst[0 * snt::SITE_THREADS] = make_float2(F[0].x, F[0].y);
+            dst[1 * snt::SITE_THREADS] = make_float2(F[0].z, F[1].x);
+            dst[2 * snt::SITE_THREADS] = make_float2(F[1].y, F[1].z);
+        };
+        if (role == 1) gather_b(0);
+        __syncthreads();
 
         int n_acc = 0, n_rej = 0, n_vac = 0;
 #pragma unroll 1
         for (int sp = 0; sp < 16; sp++) {
-            const int cx = sp >> 2, cy = sp & 3;
-            const int gx = x0 + cx + 4 * i, gy = y0 + cy + 4 * j, gz = z0 + 4 * k + 2 * h;
-            const int colbase = ((snt::H + cx + 4 * i) * snt::BX + (snt::H + cy + 4 * j)) * snt::NQ;
-            const float4 *pe[8];
+            if (role == 0) {
+                const int cx = sp >> 2, cy = sp & 3;
+                const int gx = x0 + cx + 4 * i, gy = y0 + cy + 4 * j, gz = z0 + 4 * k + 2 * h;
+                const int colbase = ((snt::H + cx + 4 * i) * snt::BX + (snt::H + cy + 4 * j)) * snt::NQ;
+                const float4 *pe[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) pe[e] = tile + colbase + zoff[e];
-
-            // trial orientations for the 2 sites (Philox keyed by global site, replica, sweep)
-            float3 np[2]; float ua[2];
+                for (int e = 0; e < 8; e++) pe[e] = tile + colbase + zoff[e];
+                float3 F[2], Gc[2];
+                float4 old[2];
+#ifdef SN_EXP_NOGA
+                sn_tile_gather2<0u, true, SPECIES>(pe, F, Gc, old);
+#else
+                sn_tile_gather2<snt::MASK_A, true, SPECIES>(pe, F, Gc, old);
+#endif
+                {
+                    const float2 *src = xF + (sp & 1) * 3 * snt::SITE_THREADS + tl;
+                    const float2 v0 = src[0 * snt::SITE_THREADS], v1 = src[1 * snt::SITE_THREADS], v2 = src[2 * snt::SITE_THREADS];
+                    F[0].x += v0.x; F[0].y += v0.y; F[0].z += v1.x; F[1].x += v1.y; F[1].y += v2.x; F[1].z += v2.y;
+                }
+                float3 np[2]; float ua[2];
 #pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const unsigned long long gsite = ((unsigned long long)gx * G.Y + gy) * G.Z + (G.z0 + gz + s);
-                const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ ((uint32_t)rep << 8),
-                                                   a.sweep_lo, a.sweep_hi, a.key0, a.key1);
-                np[s] = sn_propose(tm, sn_u01(r.x), sn_u01(r.y));
-                ua[s] = sn_u01(r.z);
+                for (int s = 0; s < 2; s++) {
+                    const float4 pr = xP[((sp & 1) * 2 + s) * snt::SITE_THREADS + tl];
+                    np[s] = make_float3(pr.x, pr.y, pr.z); ua[s] = pr.w;
+                }
+                // The 4 sites of a segment interact: decide them in z order.  Step t belongs to the lane with
+                // h == t/2 (local site t&1); its accepted change dp is broadcast to the partner lane and to the
+                // segment below (which sees it as "the segment above"), and enters the dE of the later sites as
+                //   l_i dp_i . T(0,0,dz) (l_j dp_j),  T(0,0,dz) = diag(1,1,-2)/|dz|^3,   plus the cage term for |dz| = 1.
+                // Everything that does not depend on earlier decisions (dE0, q, cg) is computed up front, so the
+                // sequential part is one short dot product, the accept test and six independent shuffles per step.
+                float3 dpp[2], q[2], cg[2];
+                float dE0[2];
+                bool vac[2];
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const float4 o = old[s];
+                    vac[s] = o.w == 0.0f;                                                      // montecarlo-core.c:163
+                    dpp[s] = make_float3(np[s].x - o.x, np[s].y - o.y, np[s].z - o.z);
+                    dE0[s] = sn_delta_e(o, np[s], F[s], Gc[s], tm);
+                    q[s] = make_float3(o.w * dpp[s].x, o.w * dpp[s].y, -2.0f * o.w * dpp[s].z);
+                    cg[s] = make_float3(-tm.cage * dpp[s].x, -tm.cage * dpp[s].y, -tm.cage * dpp[s].z);
+                }
+                const long long gidx = sn_pidx(G, gx, gy, gz);
+                float3 dmS[4], dpS[4], dmU[4], dpU[4];
+                bool accepted[2] = {false, false};
+#ifdef SN_EXP_NOCHAIN
+#pragma unroll
+                for (int t4 = 0; t4 < 0; t4++) {
+#else
+#pragma unroll
+                for (int t4 = 0; t4 < 4; t4++) {
+#endif
+                    const int s = t4 & 1;
+                    float dE = dE0[s];
+#pragma unroll
+                    for (int t2 = 0; t2 < t4; t2++) {
+                        const int d1 = t4 - t2, d2 = 4 + t2 - t4;      // distance to the earlier site below / in the segment above
+                        const float w1 = d1 == 1 ? 1.0f : d1 == 2 ? 0.125f : (1.0f / 27.0f);
+                        const float w2 = d2 == 1 ? 1.0f : d2 == 2 ? 0.125f : (1.0f / 27.0f);
+                        dE = fmaf(w1, q[s].x * dmS[t2].x + q[s].y * dmS[t2].y + q[s].z * dmS[t2].z, dE);
+                        dE = fmaf(w2, q[s].x * dmU[t2].x + q[s].y * dmU[t2].y + q[s].z * dmU[t2].z, dE);
+                        if (d1 == 1) dE += cg[s].x * dpS[t2].x + cg[s].y * dpS[t2].y + cg[s].z * dpS[t2].z;
+                        if (d2 == 1) dE += cg[s].x * dpU[t2].x + cg[s].y * dpU[t2].y + cg[s].z * dpU[t2].z;
+                    }
+                    const bool mine = h == (t4 >> 1);
+                    const bool acc = mine & !vac[s] & sn_accept(dE, tm.beta, ua[s]);           // montecarlo-core.c:179 (no short-circuit: no divergence)
+                    const float3 dp = acc ? dpp[s] : make_float3(0.f, 0.f, 0.f);
+                    if (acc) *const_cast<float4 *>(pe[3 + s]) = make_float4(np[s].x, np[s].y, np[s].z, old[s].w);
+                    accepted[s] = accepted[s] | acc;
+                    n_acc += acc; n_rej += (mine & !acc & !vac[s]); n_vac += (mine & vac[s]);
+                    if (t4 < 3) {
+                        const int srcS = (lane & 23) | ((t4 >> 1) << 3);            // owner of step t4 in this segment
+                        const int srcU = (((lane & 23) + 1) & 31) | ((t4 >> 1) << 3);   // ... in the segment above (k + 1)
+                        dpS[t4].x = __shfl_sync(0xffffffffu, dp.x, srcS);
+                        dpS[t4].y = __shfl_sync(0xffffffffu, dp.y, srcS);
+                        dpS[t4].z = __shfl_sync(0xffffffffu, dp.z, srcS);
+                        dpU[t4].x = __shfl_sync(0xffffffffu, dp.x, srcU);
+                        dpU[t4].y = __shfl_sync(0xffffffffu, dp.y, srcU);
+                        dpU[t4].z = __shfl_sync(0xffffffffu, dp.z, srcU);
+                        if constexpr (SPECIES) {
+                            const float lS = __shfl_sync(0xffffffffu, old[s].w, srcS), lU = __shfl_sync(0xffffffffu, old[s].w, srcU);
+                            dmS[t4] = make_float3(lS * dpS[t4].x, lS * dpS[t4].y, lS * dpS[t4].z);
+                            dmU[t4] = make_float3(lU * dpU[t4].x, lU * dpU[t4].y, lU * dpU[t4].z);
+                        } else { dmS[t4] = dpS[t4]; dmU[t4] = dpU[t4]; }
+                        if (k == 3) { dpU[t4] = make_float3(0.f, 0.f, 0.f); dmU[t4] = make_float3(0.f, 0.f, 0.f); }   // above lies the static halo
+                    }
+                }
+                // accepted moves go straight to global memory; tiles on a face also write the ghost images
+                // (periodic copies / the neighbouring GPU's ghost planes)
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+#ifdef SN_EXP_NOSTORE
+                    if (accepted[s] && gidx < 0) {
+#else
+                    if (accepted[s]) {
+#endif
+                        const float4 nv = make_float4(np[s].x, np[s].y, np[s].z, old[s].w);
+                        if (face_tile) sn_store_site(glat, plo, phi, G, gx, gy, gz + s, nv);
+                        else glat[gidx + s] = nv;
+                    }
+                }
+            } else if (sp < 15) {
+                // one super-pass ahead of the chain: none of role B's columns belongs to the class being updated
+                gather_b(sp + 1);
+                draw(sp + 1);
             }
-
-            float3 F[2], Gc[2];
-            float4 old[2];
-#pragma unroll
-            for (int s = 0; s < 2; s++) { F[s] = make_float3(0.f, 0.f, 0.f); Gc[s] = make_float3(0.f, 0.f, 0.f); }
-            sn_tile_gather2<SPECIES>(pe, F, Gc, old);
-
-            // The 4 sites of a segment interact: decide them in z order.  Step t belongs to the lane with
-            // h == t/2 (local site t&1); its accepted change is broadcast to the partner lane (lane^8) and to
-            // the segment below (lane-1 reads lane's value as "the segment above"), and folded into the
-            // fields of the later sites: T(0,0,dz) = diag(1,1,-2)/|dz|^3, cage term for |dz| = 1.
-            float3 dmS[4], dpS[4], dmU[4], dpU[4];
-            bool accepted[2] = {false, false};
-#pragma unroll
-            for (int t4 = 0; t4 < 4; t4++) {
-                const int s = t4 & 1;
-                float3 Fs = F[s], Gs = Gc[s];
-#pragma unroll
-                for (int t2 = 0; t2 < t4; t2++) {                 // earlier sites of this segment, dz = t2 - t4
-                    const int d = t4 - t2;
-                    const float w3 = d == 1 ? 1.0f : d == 2 ? 0.125f : (1.0f / 27.0f);
-                    Fs.x = fmaf(w3, dmS[t2].x, Fs.x); Fs.y = fmaf(w3, dmS[t2].y, Fs.y); Fs.z = fmaf(-2.0f * w3, dmS[t2].z, Fs.z);
-                    if (d == 1) { Gs.x += dpS[t2].x; Gs.y += dpS[t2].y; Gs.z += dpS[t2].z; }
-                }
-#pragma unroll
-                for (int t2 = 0; t2 < t4; t2++) {                 // earlier sites of the segment above, dz = 4 + t2 - t4
-                    const int d = 4 + t2 - t4;
-                    const float w3 = d == 1 ? 1.0f : d == 2 ? 0.125f : (1.0f / 27.0f);
-                    Fs.x = fmaf(w3, dmU[t2].x, Fs.x); Fs.y = fmaf(w3, dmU[t2].y, Fs.y); Fs.z = fmaf(-2.0f * w3, dmU[t2].z, Fs.z);
-                    if (d == 1) { Gs.x += dpU[t2].x; Gs.y += dpU[t2].y; Gs.z += dpU[t2].z; }
-                }
-                const float4 o = old[s];
-                const bool mine = h == (t4 >> 1);
-                const bool vacant = o.w == 0.0f;                                            // montecarlo-core.c:163
-                const float dE = sn_delta_e(o, np[s], Fs, Gs, tm);
-                const bool acc = mine && !vacant && sn_accept(dE, tm.beta, ua[s]);          // montecarlo-core.c:179
-                float3 dp = acc ? make_float3(np[s].x - o.x, np[s].y - o.y, np[s].z - o.z) : make_float3(0.f, 0.f, 0.f);
-                if (acc) *const_cast<float4 *>(pe[3 + s]) = make_float4(np[s].x, np[s].y, np[s].z, o.w);
-                if (mine) accepted[s] = acc;
-                n_acc += acc; n_rej += (mine && !acc && !vacant); n_vac += (mine && vacant);
-                if (t4 < 3) {
-                    const int src = (lane & 23) | ((t4 >> 1) << 3);                        // the lane that owns step t4
-                    dpS[t4].x = __shfl_sync(0xffffffffu, dp.x, src);
-                    dpS[t4].y = __shfl_sync(0xffffffffu, dp.y, src);
-                    dpS[t4].z = __shfl_sync(0xffffffffu, dp.z, src);
-                    if constexpr (SPECIES) {
-                        const float ow = __shfl_sync(0xffffffffu, o.w, src);
-                        dmS[t4] = make_float3(ow * dpS[t4].x, ow * dpS[t4].y, ow * dpS[t4].z);
-                    } else dmS[t4] = dpS[t4];
-                    dpU[t4].x = __shfl_down_sync(0xffffffffu, dpS[t4].x, 1);
-                    dpU[t4].y = __shfl_down_sync(0xffffffffu, dpS[t4].y, 1);
-                    dpU[t4].z = __shfl_down_sync(0xffffffffu, dpS[t4].z, 1);
-                    if constexpr (SPECIES) {
-                        dmU[t4].x = __shfl_down_sync(0xffffffffu, dmS[t4].x, 1);
-                        dmU[t4].y = __shfl_down_sync(0xffffffffu, dmS[t4].y, 1);
-                        dmU[t4].z = __shfl_down_sync(0xffffffffu, dmS[t4].z, 1);
-                    } else dmU[t4] = dpU[t4];
-                    if (k == 3) { dpU[t4] = make_float3(0.f, 0.f, 0.f); dmU[t4] = make_float3(0.f, 0.f, 0.f); }   // above lies the static halo
-                }
-            }
-            // accepted moves go straight to global memory (and to every ghost image / the neighbour GPU)
-#pragma unroll 1
-            for (int s = 0; s < 2; s++)
-                if (s == 0 ? accepted[0] : accepted[1])
-                    sn_store_site(glat, plo, phi, G, gx, gy, gz + s, make_float4(s == 0 ? np[0].x : np[1].x, s == 0 ? np[0].y : np[1].y,
-                                                                                 s == 0 ? np[0].z : np[1].z, s == 0 ? old[0].w : old[1].w));
             __syncthreads();
         }
+        if (role == 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
-            n_rej += __shfl_xor_sync(0xffffffffu, n_rej, o);
-            n_vac += __shfl_xor_sync(0xffffffffu, n_vac, o);
-        }
-        if (lane == 0) {
-            unsigned long long *c = a.counters + 3 * rep;
-            if (n_acc) atomicAdd(c + 0, (unsigned long long)n_acc);
-            if (n_rej) atomicAdd(c + 1, (unsigned long long)n_rej);
-            if (n_vac) atomicAdd(c + 2, (unsigned long long)n_vac);
+            for (int o = 16; o > 0; o >>= 1) {
+                n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+                n_rej += __shfl_xor_sync(0xffffffffu, n_rej, o);
+                n_vac += __shfl_xor_sync(0xffffffffu, n_vac, o);
+            }
+            if (lane == 0) {
+                unsigned long long *c = a.counters + 3 * rep;
+                if (n_acc) atomicAdd(c + 0, (unsigned long long)n_acc);
+                if (n_rej) atomicAdd(c + 1, (unsigned long long)n_rej);
+                if (n_vac) atomicAdd(c + 2, (unsigned long long)n_vac);
+            }
         }
     }
 }
