@@ -1,0 +1,400 @@
+/* starrynight_b200_main.c -- the B200 driver: StarryNight's main() with the Metropolis
+ * hot path and the lattice-wide observables running on the GPU.
+ *
+ * It keeps the reference driver's contract (/root/reference/src/starrynight-main.c):
+ *   - reads ./starrynight.cfg with the same libconfig keys and type rules
+ *     (starrynight-config.c:98-182), through driver/sn_cfg.h;
+ *   - argv[1] overrides T, argv[2] overrides CageStrain (main.c:142-151);
+ *   - same flow: initial lattice + solid solution -> initial analysis -> MCEqmSteps
+ *     equilibration mega-steps -> MCMegaSteps production mega-steps, each followed by
+ *     the mid-point analysis (main.c:180-265);
+ *   - same output files and formats: Recombination_T_%04d.log, rdf.dat,
+ *     initial_lattice_potential.{xyz,cube}, initial_pot.png, equilib_pot.png and
+ *     T_%04d_%d_%03d{-RDF.dat,_potential.xyz,_potential.cube,_potential.png,_MC-PNG.png,_MC-SVG.svg}.
+ * What changes is who does the work: every call into montecarlo-core.c / analysis.c
+ * becomes a call into libstarrynight_b200.so (include/starrynight_b200.h).  There is
+ * no CPU fallback; without a usable GPU the driver stops with an error.
+ *
+ * Optional extra keys (absent in the stock cfg, so it runs unchanged):
+ *   Seed (int)          Philox / MT seed instead of 0xDEADBEEF + T
+ *   Device (int)        CUDA device ordinal
+ *   Kernel (string)     "auto" | "colour" | "tiled"
+ *   Hysteresis : { amplitude = 0.1; steps = 64; cycles = 1; }   triangular Efield.x ramp after
+ *                       equilibration (the loop main.c:229-238 only has commented out); prints
+ *                       "T: %d Efield: x %f Polar: %f" per field point (main.c:82)
+ * Terminal art (outputlattice_dumb_terminal) and the recombination model are not part of the
+ * accelerated path and are reported as skipped.
+ *
+ *   --init-only FILE    build the initial lattice exactly as the run would, write it as raw
+ *                       float[X][Y][Z][4] to FILE and exit before touching the GPU (used by tests).
+ */
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../include/starrynight_b200.h"
+#include "sn_cfg.h"
+#include "sn_lattice_init.h"
+
+/* ---- run parameters, names as in starrynight-config.c:12-93 ------------------ */
+static int X = 20, Y = 20, Z = 20, DIM = 3, T = 0;
+static double Efield[3] = {0, 0, 0}, K = 1.0, CageStrain = 1.0, MCMegaMultiplier = 1.0;
+static int DipoleCutOff = 3, MCMegaSteps = 400, MCEqmSteps = 10, ConstrainToX = 0;
+static int DisplayDumbTerminal = 1, CalculateRecombination = 1, CalculateRadialOrderParameter = 0;
+static int CalculatePotential = 0, CalculateEfield = 0, SaveDipolesXYZ = 0, SaveDipolesPNG = 0, SaveDipolesSVG = 0, SavePotentialCube = 0;
+static const char *InitialLattice = "random";
+static float dip_length[10], dip_prevalence[10];
+static int dipolecount = 0;
+static long long seed_override = -1;
+static int device = 0, kernel = SN_KERNEL_AUTO;
+static double hyst_amplitude = 0.0;
+static int hyst_steps = 0, hyst_cycles = 1;
+
+static void die(const char *what)
+{
+    fprintf(stderr, "starrynight-b200: %s: %s\n", what, sn_last_error());
+    exit(EXIT_FAILURE);
+}
+#define SN(call) do { if ((call) != SN_OK) die(#call); } while (0)
+
+static void load_config(const char *path)
+{
+    snc_config cfg;
+    const snc_node *s;
+    double tmp;
+    const char *str;
+    int i;
+    snc_init(&cfg);
+    if (!snc_read_file(&cfg, path)) {                                   /* config.c:113-121 */
+        fprintf(stderr, "%s:%d - %s\n", cfg.err_file, cfg.err_line, cfg.err_text);
+        exit(EXIT_FAILURE);
+    }
+    snc_lookup_int(&cfg, "T", &T);
+    snc_lookup_int(&cfg, "X", &X); snc_lookup_int(&cfg, "Y", &Y); snc_lookup_int(&cfg, "Z", &Z);
+    if (snc_lookup_float(&cfg, "Efield.x", &tmp)) Efield[0] = (float)tmp;  /* stored as float, config.c:132 */
+    if (snc_lookup_float(&cfg, "Efield.y", &tmp)) Efield[1] = (float)tmp;
+    if (snc_lookup_float(&cfg, "Efield.z", &tmp)) Efield[2] = (float)tmp;
+    fprintf(stderr, "Efield: x %f y %f z %f\n", Efield[0], Efield[1], Efield[2]);
+    snc_lookup_float(&cfg, "K", &K);
+    snc_lookup_float(&cfg, "CageStrain", &CageStrain);
+    fprintf(stderr, "CageStrain: %f\n", CageStrain);
+    s = snc_lookup(&cfg, "Dipoles");
+    dipolecount = snc_length(s);
+    if (dipolecount > 10) dipolecount = 10;
+    for (i = 0; i < dipolecount; i++) dip_length[i] = (float)snc_get_float_elem(s, i);
+    s = snc_lookup(&cfg, "Prevalence");
+    dipolecount = snc_length(s);                                         /* config.c:148: the second list decides */
+    if (dipolecount > 10) dipolecount = 10;
+    for (i = 0; i < dipolecount; i++) dip_prevalence[i] = (float)snc_get_float_elem(s, i);
+    for (i = 0; i < dipolecount; i++) fprintf(stderr, "Dipole: %d Length: %f Prevalence: %f\n", i, dip_length[i], dip_prevalence[i]);
+    snc_lookup_bool(&cfg, "ConstrainToX", &ConstrainToX);
+    snc_lookup_int(&cfg, "DipoleCutOff", &DipoleCutOff);
+    if (snc_lookup_string(&cfg, "InitialLattice", &str)) InitialLattice = strdup(str);
+    snc_lookup_int(&cfg, "MCEqmSteps", &MCEqmSteps);
+    snc_lookup_int(&cfg, "MCMegaSteps", &MCMegaSteps);
+    snc_lookup_float(&cfg, "MCMoves", &MCMegaMultiplier);
+    snc_lookup_bool(&cfg, "DisplayDumbTerminal", &DisplayDumbTerminal);
+    snc_lookup_bool(&cfg, "CalculateRecombination", &CalculateRecombination);
+    snc_lookup_bool(&cfg, "CalculateRadialOrderParameter", &CalculateRadialOrderParameter);
+    snc_lookup_bool(&cfg, "CalculatePotential", &CalculatePotential);
+    snc_lookup_bool(&cfg, "CalculateEfield", &CalculateEfield);
+    snc_lookup_bool(&cfg, "SaveDipolesSVG", &SaveDipolesSVG);
+    snc_lookup_bool(&cfg, "SaveDipolesPNG", &SaveDipolesPNG);
+    snc_lookup_bool(&cfg, "SaveDipolesXYZ", &SaveDipolesXYZ);
+    snc_lookup_bool(&cfg, "SavePotentialCube", &SavePotentialCube);
+    /* optional B200 keys */
+    if (snc_lookup_int(&cfg, "Seed", &i)) seed_override = (unsigned int)i;
+    snc_lookup_int(&cfg, "Device", &device);
+    if (snc_lookup_string(&cfg, "Kernel", &str))
+        kernel = !strcmp(str, "colour") ? SN_KERNEL_COLOUR : !strcmp(str, "tiled") ? SN_KERNEL_TILED : SN_KERNEL_AUTO;
+    snc_lookup_float(&cfg, "Hysteresis.amplitude", &hyst_amplitude);
+    snc_lookup_int(&cfg, "Hysteresis.steps", &hyst_steps);
+    snc_lookup_int(&cfg, "Hysteresis.cycles", &hyst_cycles);
+    fprintf(stderr, "Finished loading config file. \n");
+    /* strings were strdup'ed; the tree can go */
+    snc_destroy(&cfg);
+}
+
+/* ---- writers: formats of starrynight-analysis.c --------------------------------- */
+static size_t site(int x, int y, int z) { return ((size_t)x * Y + y) * Z + z; }
+
+static void write_potential_xyz(const char *fn, const double *V)          /* analysis.c:264-276 */
+{
+    FILE *fo = fopen(fn, "w"); int x, y, z;
+    if (!fo) { perror(fn); return; }
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++) fprintf(fo, "%d %d %d %f\n", x, y, z, V[site(x, y, z)]);
+    fclose(fo);
+}
+
+static void write_potential_cube(const char *fn, const double *V)         /* analysis.c:280-308 */
+{
+    FILE *fo = fopen(fn, "w"); int x, y, z;
+    if (!fo) { perror(fn); return; }
+    fprintf(fo, "Starrynight Cube file: %d %d %d\n\n", X, Y, Z);
+    fprintf(fo, "1 0.0 0.0 0.0\n");
+    fprintf(fo, "%d 1.0 0.0 0.0\n", X);
+    fprintf(fo, "%d 0.0 1.0 0.0\n", Y);
+    fprintf(fo, "%d 0.0 0.0 1.0\n", Z);
+    fprintf(fo, "1 0.0 0.0 0.0 0.0 0.0\n");
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++) {
+        for (z = 0; z < Z; z++) { fprintf(fo, "%g ", V[site(x, y, z)]); if (z % 6 == 5) fprintf(fo, "\n"); }
+        fprintf(fo, "\n");
+    }
+    fclose(fo);
+}
+
+static void write_potential_png(const char *fn, const double *V)          /* analysis.c:481-504 (a P2 greymap) */
+{
+    FILE *fo = fopen(fn, "w"); int i, k, pixel;
+    if (!fo) { perror(fn); return; }
+    fprintf(fo, "P2\n%d %d\n%d\n", X, Y, SHRT_MAX);
+    for (i = 0; i < X; i++) {
+        for (k = 0; k < Y; k++) {
+            pixel = SHRT_MAX / 2 + (int)(SHRT_MAX * 0.1 * V[site(i, k, 0)]);
+            if (pixel < 0) pixel = 0;
+            if (pixel > SHRT_MAX) pixel = SHRT_MAX;
+            fprintf(fo, "%d ", pixel);
+        }
+        fprintf(fo, "\n");
+    }
+    fclose(fo);
+}
+
+static void write_rdf(const char *fn, const double *fe, const double *afe, const long long *cnt)   /* analysis.c:582-595 */
+{
+    FILE *fo = fopen(fn, "a"); int i;                                     /* append, as the reference does */
+    if (!fo) { perror(fn); return; }
+    fprintf(fo, "# r^2 r orientational_FE_correlation[r^2] orientational_AFE_correlation[r^2] orientational_count[r^2] T\n");
+    for (i = 0; i < SN_RDF_BINS; i++)
+        if (cnt[i] > 0) fprintf(fo, "%d %f %f %f %lld %d\n", i, sqrt((double)i), fe[i] / (double)cnt[i], afe[i] / (double)cnt[i], cnt[i], T);
+    fprintf(fo, "\n");
+    fclose(fo);
+}
+
+static void write_lattice_xyz(const char *fn, const float *lat)           /* analysis.c:710-728 */
+{
+    FILE *fo = fopen(fn, "w"); int x, y, z; const float r = 1.6f / 2, d = 4.0f; const double ZSCALE = 5.0;
+    if (!fo) { perror(fn); return; }
+    fprintf(fo, "%d\n\n", X * Y * Z * 2);
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++) {
+        const float *p = lat + site(x, y, z) * 4;
+        fprintf(fo, "C %f %f %f\n", d * x + r * p[0], d * y + r * p[1], ZSCALE * (d * z) + r * p[2]);
+        fprintf(fo, "N %f %f %f\n", d * x - r * p[0], d * y - r * p[1], ZSCALE * (d * z) - r * p[2]);
+    }
+    fclose(fo);
+}
+
+static void write_lattice_svg(const char *fn, const float *lat)           /* analysis.c:675-706, z = 0 slice */
+{
+    FILE *fo = fopen(fn, "w"); int x, y;
+    if (!fo) { perror(fn); return; }
+    fprintf(fo, "<svg xmlns=\"http://www.w3.org/2000/svg\" version=\"1.1\" height=\"%d\" width=\"%d\">\n", X, Y);
+    fprintf(fo, " <marker id=\"triangle\" viewBox=\"0 0 10 10\" refX=\"7\" refY=\"5\" markerUnits=\"strokeWidth\" markerWidth=\"2\" markerHeight=\"2\" orient=\"auto\"><path d=\"M 0 0 L 10 5 L 0 10 z\" /></marker>\n");
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++) {
+        const float *p = lat + site(x, y, 0) * 4; const int g = (int)((-p[2] + 1.0) * 127.0);
+        fprintf(fo, " <line x1=\"%f\" y1=\"%f\" x2=\"%f\" y2=\"%f\" style=\"stroke:rgb(%d,%d,%d);stroke-width:0.17\" marker-end=\"url(#triangle)\" />\n",
+                y + 0.5 + 0.4 * p[1], x + 0.5 + 0.4 * p[0], y + 0.5 - 0.4 * p[1], x + 0.5 - 0.4 * p[0], g, g, g);
+    }
+    fprintf(fo, "</svg>\n");
+    fclose(fo);
+}
+
+static void write_lattice_ppm_hsv(const char *fn, const float *lat)       /* analysis.c:620-671, z = 0 slice */
+{
+    FILE *fo = fopen(fn, "w"); int i, k;
+    if (!fo) { perror(fn); return; }
+    fprintf(fo, "P6\n%d %d\n255\n", X, Y);
+    for (i = 0; i < X; i++) for (k = 0; k < Y; k++) {
+        const float *d = lat + site(i, k, 0) * 4;
+        float h = M_PI + atan2(d[1], d[0]), v = 0.5 + 0.4 * d[2], s = 0.6 - 0.6 * fabs(d[2]), r = 0, g = 0, b = 0, f, p, q, t;
+        int hp = (int)floor(h / (M_PI / 3.0));
+        f = h / (M_PI / 3.0) - (float)hp;
+        p = v * (1.0 - s); q = v * (1.0 - f * s); t = v * (1.0 - (1.0 - f) * s);
+        switch (hp) { case 0: r = v; g = t; b = p; break; case 1: r = q; g = v; b = p; break; case 2: r = p; g = v; b = t; break;
+                      case 3: r = p; g = q; b = v; break; case 4: r = t; g = p; b = v; break; case 5: r = v; g = p; b = q; break; }
+        if (d[0] == 0.0 && d[1] == 0.0 && d[2] == 0.0) { r = 0; g = 0; b = 0; }
+        fprintf(fo, "%c%c%c", (char)(254.0 * r), (char)(254.0 * g), (char)(254.0 * b));
+    }
+    fclose(fo);
+}
+
+/* ---- analysis hooks, main.c:29-122 ------------------------------------------------ */
+static double *Vbuf;
+static float *latbuf;
+
+static void refresh_potential(sn_handle *h) { SN(sn_potential_map(h, 0, Vbuf)); }
+
+static void do_rdf(sn_handle *h, const char *fn)
+{
+    double fe[SN_RDF_BINS], afe[SN_RDF_BINS]; long long cnt[SN_RDF_BINS];
+    SN(sn_rdf(h, 0, fe, afe, cnt));
+    write_rdf(fn, fe, afe, cnt);
+}
+
+static void terminal_summary(void)
+{
+    /* the last line outputlattice_dumb_terminal prints (analysis.c:923-925), from the z = 0 slice of V */
+    int x, y; double mean = 0, var = 0, dmax = 0;
+    for (y = 0; y < Y; y++) for (x = 0; x < X; x++) { double p = Vbuf[site(x, y, 0)]; mean += p; var += p * p; if (fabs(p) > dmax) dmax = fabs(p); }
+    fprintf(stderr, "T: %d DMAX: %f new_DMAX: %f variance: %f mean: %f\n", T, dmax, dmax, var / (X * Y), mean / (X * Y));
+}
+
+static void analysis_initial(sn_handle *h)                                 /* main.c:29-48 */
+{
+    int need_v = CalculatePotential || SavePotentialCube || DisplayDumbTerminal;
+    if (CalculateEfield) fprintf(stderr, "CalculateEfield: E-field maps are outside the accelerated path, skipped\n");
+    if (need_v) refresh_potential(h);
+    if (CalculatePotential) write_potential_xyz("initial_lattice_potential.xyz", Vbuf);
+    if (SavePotentialCube) write_potential_cube("initial_lattice_potential.cube", Vbuf);
+    if (SaveDipolesSVG || SaveDipolesPNG || SaveDipolesXYZ) SN(sn_get_lattice(h, 0, latbuf));
+    if (SaveDipolesSVG) write_lattice_svg("initial-SVG.svg", latbuf);
+    if (CalculatePotential) write_potential_png("initial_pot.png", Vbuf);
+    if (SaveDipolesXYZ) write_lattice_xyz("initial_dipoles.xyz", latbuf);
+    if (CalculateRadialOrderParameter) do_rdf(h, "rdf.dat");
+    if (SaveDipolesPNG) write_lattice_ppm_hsv("initial.png", latbuf);
+    if (DisplayDumbTerminal) terminal_summary();
+    if (CalculateRecombination) fprintf(stderr, "CalculateRecombination: the recombination model is outside the accelerated path, skipped\n");
+}
+
+static void analysis_midpoint(sn_handle *h, int MCstep)                    /* main.c:51-103 */
+{
+    char name[160], prefix[100];
+    int need_v = CalculatePotential || SavePotentialCube || DisplayDumbTerminal;
+    sprintf(prefix, "T_%04d_%d_%03d", T, (int)CageStrain, MCstep);       /* main.c:58 */
+    if (need_v) refresh_potential(h);
+    if (DisplayDumbTerminal) terminal_summary();
+    sprintf(name, "%s-RDF.dat", prefix);
+    if (CalculateRadialOrderParameter) do_rdf(h, name);
+    sprintf(name, "%s_potential.xyz", prefix);
+    if (CalculatePotential) write_potential_xyz(name, Vbuf);
+    sprintf(name, "%s_potential.cube", prefix);
+    if (SavePotentialCube) write_potential_cube(name, Vbuf);
+    sprintf(name, "%s_potential.png", prefix);
+    if (CalculatePotential) write_potential_png(name, Vbuf);
+    if (SaveDipolesPNG || SaveDipolesSVG) SN(sn_get_lattice(h, 0, latbuf));
+    sprintf(name, "%s_MC-PNG.png", prefix);
+    if (SaveDipolesPNG) write_lattice_ppm_hsv(name, latbuf);
+    sprintf(name, "%s_MC-SVG.svg", prefix);
+    if (SaveDipolesSVG) write_lattice_svg(name, latbuf);
+}
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+int main(int argc, char *argv[])
+{
+    const char *init_only = NULL, *cfgpath = "starrynight.cfg";
+    int i, npos = 0;
+    char name[160];
+    FILE *log;
+    sn_mt19937 mt;
+    sn_params p;
+    sn_handle *h = NULL;
+    long long sweeps_per_megastep;
+    unsigned long long acc = 0, rej = 0, vac = 0;
+    size_t nsites;
+    int histo[10];
+
+    fprintf(stderr, "Starry Night - Monte Carlo brushstrokes (B200 build: %s).\n", sn_version());
+    for (i = 1; i < argc; i++)
+        if (!strcmp(argv[i], "--init-only") && i + 1 < argc) { init_only = argv[++i]; }
+        else if (!strcmp(argv[i], "--config") && i + 1 < argc) { cfgpath = argv[++i]; }
+
+    fprintf(stderr, "Loading config...\n");
+    load_config(cfgpath);
+    for (i = 1; i < argc; i++) {                                           /* main.c:142-151 */
+        if (!strcmp(argv[i], "--init-only") || !strcmp(argv[i], "--config")) { i++; continue; }
+        if (npos == 0) { sscanf(argv[i], "%d", &T); fprintf(stderr, "Command line temperature: T = %d\n", T); }
+        if (npos == 1) { sscanf(argv[i], "%lf", &CageStrain); fprintf(stderr, "Command Line CageStrain: CageStrain = %lf\n", CageStrain); }
+        npos++;
+    }
+    nsites = (size_t)X * Y * Z;
+    fprintf(stderr, "Memory allocation for lattice with X=%d Y=%d Z=%d\n", X, Y, Z);
+    latbuf = (float *)calloc(nsites * 4, sizeof(float));
+    Vbuf = (double *)calloc(nsites, sizeof(double));
+    if (!latbuf || !Vbuf) { fprintf(stderr, "out of host memory\n"); return EXIT_FAILURE; }
+
+    {   /* main.c:172-176: seed the twister with 0xDEADBEEF + T (int arithmetic wraps as there) */
+        unsigned int SEED = seed_override >= 0 ? (unsigned int)seed_override : (unsigned int)(0xDEADBEEFu + (unsigned int)T);
+        sn_mt_seed(&mt, SEED);
+        fprintf(stderr, "Mersenne Twister initialised... seed: %X\t", SEED);
+        if (!sn_init_lattice(latbuf, X, Y, Z, DIM, InitialLattice, &mt)) {
+            fprintf(stderr, "unknown InitialLattice '%s', using random (main.c:185)\n", InitialLattice);
+            sn_init_lattice(latbuf, X, Y, Z, DIM, "random", &mt);
+        }
+        fprintf(stderr, "Lattice initialised...");
+        sn_init_solid_solution(latbuf, X, Y, Z, dipolecount, dip_length, dip_prevalence, &mt, histo);
+        fprintf(stderr, "\nSolid Solution: ");
+        for (i = 0; i < dipolecount; i++) fprintf(stderr, "    Dipole %d: Length: %f Count: %d", i, dip_length[i], histo[i]);
+        fprintf(stderr, "\nSolid solution formed...\n");
+        if (init_only) {
+            FILE *f = fopen(init_only, "wb");
+            if (!f || fwrite(latbuf, sizeof(float), nsites * 4, f) != nsites * 4) { perror(init_only); return EXIT_FAILURE; }
+            fclose(f);
+            return 0;
+        }
+        sprintf(name, "Recombination_T_%04d.log", T);                      /* main.c:165-178 */
+        log = fopen(name, "w");
+        fprintf(stderr, "Log file '%s' opened. ", name);
+        if (log) fprintf(log, "# Starrynight - simulation run on time(NULL)= %ld\n# Mersenne Twister Seed: %X\n", (long)time(NULL), SEED);
+
+        SN(sn_default_params(&p));
+        p.X = X; p.Y = Y; p.Z = Z; p.cutoff = DipoleCutOff; p.CageStrain = CageStrain; p.K = K;
+        p.Efield[0] = (float)Efield[0]; p.Efield[1] = (float)Efield[1]; p.Efield[2] = (float)Efield[2];
+        p.beta = 1 / ((float)T / 300.0);                                   /* main.c:215 */
+        p.ConstrainToX = ConstrainToX; p.DIM = DIM; p.nreplicas = 1; p.seed = SEED; p.device = device; p.kernel = kernel;
+    }
+    SN(sn_create(&p, &h));                                                 /* lattice malloc + gen_neighbour, main.c:155-180 */
+    { int nnb = 0; SN(sn_neighbour_table(h, &nnb, NULL, NULL));
+      fprintf(stderr, "\nNeighbour list generated: %d neighbours found with DipoleCutOff=%d.\n", nnb, DipoleCutOff); }
+    SN(sn_set_lattice(h, 0, latbuf));
+    analysis_initial(h);
+
+    sweeps_per_megastep = (long long)(MCMegaMultiplier + 0.5);             /* MCMinorSteps = X*Y*Z*MCMoves attempts, config.c:166 */
+    if (sweeps_per_megastep < 1 && MCMegaMultiplier > 0) sweeps_per_megastep = 1;
+    fprintf(stderr, "\n\tMC startup. 'Do I dare disturb the universe?'\n");
+    fprintf(stderr, "'.' is %e MC moves attempted.\n", (double)sweeps_per_megastep * (double)nsites);
+    fprintf(stderr, "Equilibriation MC moves... %e\n", (double)sweeps_per_megastep * (double)nsites * (double)MCEqmSteps);
+    for (i = 0; i < MCEqmSteps; i++) { fprintf(stderr, ","); SN(sn_mc_sweeps(h, sweeps_per_megastep)); }   /* main.c:219-223 */
+    SN(sn_synchronize(h));
+    if (CalculatePotential) { refresh_potential(h); write_potential_png("equilib_pot.png", Vbuf); }
+    if (SaveDipolesSVG) { SN(sn_get_lattice(h, 0, latbuf)); write_lattice_svg("equilib-SVG.svg", latbuf); }
+
+    if (hyst_steps > 0 && hyst_amplitude != 0.0) {
+        /* triangular ramp 0 -> +A -> -A -> 0 of Efield.x, one mega-step of sweeps per field point */
+        int c, s; const int n = 4 * hyst_steps;
+        for (c = 0; c < hyst_cycles; c++) for (s = 0; s < n; s++) {
+            const double ph = (double)s / hyst_steps;                      /* 0..4 */
+            const double e = hyst_amplitude * (ph < 1 ? ph : ph < 3 ? 2 - ph : ph - 4);
+            float E[3] = {(float)e, (float)Efield[1], (float)Efield[2]}; double P[3];
+            SN(sn_set_efield(h, 0, E));
+            SN(sn_mc_sweeps(h, sweeps_per_megastep));
+            SN(sn_polarisation(h, 0, P));
+            fprintf(stdout, "T: %d Efield: x %f Polar: %f\n", T, e, P[0]);
+        }
+        { float E[3] = {(float)Efield[0], (float)Efield[1], (float)Efield[2]}; SN(sn_set_efield(h, 0, E)); }
+        fflush(stdout);
+    }
+
+    for (i = 0; i < MCMegaSteps; i++) {                                    /* main.c:244-265, the hot loop */
+        double tic = now_s(), toc, tac;
+        SN(sn_mc_sweeps(h, sweeps_per_megastep));
+        SN(sn_synchronize(h));
+        toc = now_s();
+        analysis_midpoint(h, i);
+        fflush(stdout);
+        tac = now_s();
+        fprintf(stderr, "MC Moves (per second): %f MHz\n", 1e-6 * (double)sweeps_per_megastep * (double)nsites / (toc - tic));
+        fprintf(stderr, "Output routines: %f s ; Efficiency of MC moves vs. analysis %.2f%%\n", tac - toc, 100.0 * (toc - tic) / (tac - tic));
+    }
+    fprintf(stderr, "\n");
+    SN(sn_get_counters(h, 0, &acc, &rej, &vac));
+    fprintf(stderr, "Monte Carlo moves - ACCEPT: %llu REJECT: %llu ratio: %f\n", acc, rej, (float)acc / (float)(rej + acc));
+    fprintf(stderr, " For us, there is only the trying. The rest is not our business. ~T.S.Eliot\n\n");
+    if (log) fclose(log);
+    SN(sn_destroy(h));
+    free(latbuf); free(Vbuf);
+    return 0;
+}

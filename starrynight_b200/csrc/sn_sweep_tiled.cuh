@@ -259,27 +259,28 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         zoff[e] = (w & 3) * snt::BOX_STRIDE_F4 + (w >> 2);
     }
 
+    // TMA load of tile t into shared memory (4 residue boxes), completion on the mbarrier
+    auto issue_tile_load = [&](long long t) {
+        const int iz = (int)(t % ph.hz), iy = (int)((t / ph.hz) % ph.hy), ix = (int)((t / ((long long)ph.hz * ph.hy)) % ph.hx);
+        const int rep = (int)(t / ((long long)ph.hz * ph.hy * ph.hx));
+        const int x0 = (2 * ix + ph.px) * snt::T, y0 = (2 * iy + ph.py) * snt::T, z0 = (2 * iz + ph.pz) * snt::T;
+        // shared memory was last touched through the generic proxy; order it before the async-proxy writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4 * snt::BOX_BYTES) : "memory");
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t dst = sn_smem_u32(smem) + r * snt::BOX_STRIDE_F4 * 16;
+            // padded coordinates: x0-3 -> x0, y0-3 -> y0, window start z0-4+r -> z0-1+r (ghost width 3)
+            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                         ::"r"(dst), "l"(&tmap), "r"(0), "r"(z0 - 1 + r), "r"(y0), "r"(x0), "r"(rep), "r"(bar) : "memory");
+        }
+    };
+    if (tid == 0 && blockIdx.x < ntiles) issue_tile_load(blockIdx.x);
+
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int iz = (int)(t % ph.hz), iy = (int)((t / ph.hz) % ph.hy), ix = (int)((t / ((long long)ph.hz * ph.hy)) % ph.hx);
         const int rep = (int)(t / ((long long)ph.hz * ph.hy * ph.hx));
         const int x0 = (2 * ix + ph.px) * snt::T, y0 = (2 * iy + ph.py) * snt::T, z0 = (2 * iz + ph.pz) * snt::T;
-
-#ifdef SN_EXP_NOTMA
-        if (tid == 0 && t == blockIdx.x) {
-#else
-        if (tid == 0) {
-#endif
-            // shared memory was last touched through the generic proxy; order it before the async-proxy writes
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4 * snt::BOX_BYTES) : "memory");
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const uint32_t dst = sn_smem_u32(smem) + r * snt::BOX_STRIDE_F4 * 16;
-                // padded coordinates: x0-3 -> x0, y0-3 -> y0, window start z0-4+r -> z0-1+r (ghost width 3)
-                asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                             ::"r"(dst), "l"(&tmap), "r"(0), "r"(z0 - 1 + r), "r"(y0), "r"(x0), "r"(rep), "r"(bar) : "memory");
-            }
-        }
 
         SnTerms tm;
         tm.cage = a.cage; tm.K = a.K; tm.beta = a.beta[rep];
@@ -309,24 +310,8 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         };
         if (role == 1) draw(0);                          // overlaps the TMA flight
 
-#ifdef SN_EXP_NOTMA
-        if (t == blockIdx.x) { sn_mbar_wait(bar, parity); parity ^= 1; }
-#else
         sn_mbar_wait(bar, parity);
         parity ^= 1;
-#endif
-
-        if (tid == 32 && t + gridDim.x < ntiles) {
-            // pull the next tile's boxes into L2 while this one is being swept
-            const long long t2 = t + gridDim.x;
-            const int jz = (int)(t2 % ph.hz), jy = (int)((t2 / ph.hz) % ph.hy), jx = (int)((t2 / ((long long)ph.hz * ph.hy)) % ph.hx);
-            const int rep2 = (int)(t2 / ((long long)ph.hz * ph.hy * ph.hx));
-            const int nx0 = (2 * jx + ph.px) * snt::T, ny0 = (2 * jy + ph.py) * snt::T, nz0 = (2 * jz + ph.pz) * snt::T;
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-                asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
-                             ::"l"(&tmap), "r"(0), "r"(nz0 - 1 + r), "r"(ny0), "r"(nx0), "r"(rep2) : "memory");
-        }
 
         // role B's share of the fields of super-pass sp, left in xF[sp & 1]
         auto gather_b = [&](int sp) {
@@ -395,9 +380,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                     q[s] = make_float3(o.w * dpp[s].x, o.w * dpp[s].y, -2.0f * o.w * dpp[s].z);
                     cg[s] = make_float3(-tm.cage * dpp[s].x, -tm.cage * dpp[s].y, -tm.cage * dpp[s].z);
                 }
-                const long long gidx = sn_pidx(G, gx, gy, gz);
                 float3 dmS[4], dpS[4], dmU[4], dpU[4];
-                bool accepted[2] = {false, false};
 #ifdef SN_EXP_NOCHAIN
 #pragma unroll
                 for (int t4 = 0; t4 < 0; t4++) {
@@ -418,20 +401,29 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                         if (d2 == 1) dE += cg[s].x * dpU[t2].x + cg[s].y * dpU[t2].y + cg[s].z * dpU[t2].z;
                     }
                     const bool mine = h == (t4 >> 1);
+#ifdef SN_EXP_NOEXP
+                    const bool acc = mine & !vac[s] & (dE < 0.0f);
+#else
                     const bool acc = mine & !vac[s] & sn_accept(dE, tm.beta, ua[s]);           // montecarlo-core.c:179 (no short-circuit: no divergence)
+#endif
                     const float3 dp = acc ? dpp[s] : make_float3(0.f, 0.f, 0.f);
+#ifndef SN_EXP_NOSTS
                     if (acc) *const_cast<float4 *>(pe[3 + s]) = make_float4(np[s].x, np[s].y, np[s].z, old[s].w);
-                    accepted[s] = accepted[s] | acc;
+#endif
                     n_acc += acc; n_rej += (mine & !acc & !vac[s]); n_vac += (mine & vac[s]);
                     if (t4 < 3) {
                         const int srcS = (lane & 23) | ((t4 >> 1) << 3);            // owner of step t4 in this segment
                         const int srcU = (((lane & 23) + 1) & 31) | ((t4 >> 1) << 3);   // ... in the segment above (k + 1)
+#ifdef SN_EXP_NOSHFL
+                        dpS[t4] = dp; dpU[t4] = make_float3(dp.y, dp.z, dp.x); (void)srcS; (void)srcU;
+#else
                         dpS[t4].x = __shfl_sync(0xffffffffu, dp.x, srcS);
                         dpS[t4].y = __shfl_sync(0xffffffffu, dp.y, srcS);
                         dpS[t4].z = __shfl_sync(0xffffffffu, dp.z, srcS);
                         dpU[t4].x = __shfl_sync(0xffffffffu, dp.x, srcU);
                         dpU[t4].y = __shfl_sync(0xffffffffu, dp.y, srcU);
                         dpU[t4].z = __shfl_sync(0xffffffffu, dp.z, srcU);
+#endif
                         if constexpr (SPECIES) {
                             const float lS = __shfl_sync(0xffffffffu, old[s].w, srcS), lU = __shfl_sync(0xffffffffu, old[s].w, srcU);
                             dmS[t4] = make_float3(lS * dpS[t4].x, lS * dpS[t4].y, lS * dpS[t4].z);
@@ -440,26 +432,35 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                         if (k == 3) { dpU[t4] = make_float3(0.f, 0.f, 0.f); dmU[t4] = make_float3(0.f, 0.f, 0.f); }   // above lies the static halo
                     }
                 }
-                // accepted moves go straight to global memory; tiles on a face also write the ghost images
-                // (periodic copies / the neighbouring GPU's ghost planes)
-#pragma unroll
-                for (int s = 0; s < 2; s++) {
-#ifdef SN_EXP_NOSTORE
-                    if (accepted[s] && gidx < 0) {
-#else
-                    if (accepted[s]) {
-#endif
-                        const float4 nv = make_float4(np[s].x, np[s].y, np[s].z, old[s].w);
-                        if (face_tile) sn_store_site(glat, plo, phi, G, gx, gy, gz + s, nv);
-                        else glat[gidx + s] = nv;
-                    }
-                }
             } else if (sp < 15) {
                 // one super-pass ahead of the chain: none of role B's columns belongs to the class being updated
                 gather_b(sp + 1);
                 draw(sp + 1);
             }
             __syncthreads();
+        }
+        // Write the tile's 16^3 interior back: shared memory -> registers, then (once everybody has read) the
+        // TMA load of the next tile is started and the registers are stored to global memory underneath it.
+        // Lanes run along z, so a half-warp writes one 256-byte row.  Sites on a lattice / slab face also go
+        // to their ghost images (periodic copies, or the neighbouring GPU's ghost planes over NVLink).
+        {
+            float4 wb[16];
+            const int lz = tid & 15, row0 = tid >> 4;
+            const int zo = ((lz + 4) & 3) * snt::BOX_STRIDE_F4 + ((lz + 4) >> 2);
+#pragma unroll
+            for (int pss = 0; pss < 16; pss++) {
+                const int row = pss * 16 + row0, lx = row >> 4, ly = row & 15;
+                wb[pss] = tile[((lx + snt::H) * snt::BX + (ly + snt::H)) * snt::NQ + zo];
+            }
+            __syncthreads();
+            if (tid == 0 && t + gridDim.x < ntiles) issue_tile_load(t + gridDim.x);
+            const long long gbase = sn_pidx(G, x0, y0, z0 + lz);
+#pragma unroll
+            for (int pss = 0; pss < 16; pss++) {
+                const int row = pss * 16 + row0, lx = row >> 4, ly = row & 15;
+                if (face_tile) sn_store_site(glat, plo, phi, G, x0 + lx, y0 + ly, z0 + lz, wb[pss]);
+                else glat[gbase + lx * G.sx + ly * G.sy] = wb[pss];
+            }
         }
         if (role == 0) {
 #pragma unroll

@@ -104,6 +104,23 @@ def main():
     re1 = np.array([r.lib.ref_genrand_real1() for _ in range(8)])
     re2 = np.array([r.lib.ref_genrand_real2() for _ in range(8)])
     np.savez_compressed(os.path.join(HERE, "mt19937.npz"), int32_seed5489=mt, real1=re1, real2=re2)
+    # the reference PROGRAM on a shortened copy of its own starrynight.cfg: the files its main() writes
+    import shutil
+    import subprocess
+    work = tempfile.mkdtemp()
+    cfg = open(os.path.join(oa.REF_ROOT, "starrynight.cfg")).read()
+    cfg = cfg.replace("MCMegaSteps: 20", "MCMegaSteps: 1").replace("MCEqmSteps: 5", "MCEqmSteps: 1").replace("MCMoves: 200.0", "MCMoves: 2.0")
+    cfg = cfg.replace("DisplayDumbTerminal: true", "DisplayDumbTerminal: false")
+    open(os.path.join(work, "starrynight.cfg"), "w").write(cfg)
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "starrynight_ref")], cwd=work, check=True, capture_output=True)
+    files = {}
+    for fn in sorted(os.listdir(work)):
+        if fn.startswith("Recombination"):
+            continue                     # carries time(NULL)
+        files[fn] = np.frombuffer(open(os.path.join(work, fn), "rb").read(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "reference_run_files.npz"), **files)
+    print("reference run files:", ", ".join(f"{k} ({len(v)} B)" for k, v in files.items()))
+    shutil.rmtree(work)
     print("done")
 
 
