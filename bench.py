@@ -175,16 +175,30 @@ def synthetic_slab(size, z0, nz, seed=1234):
     import torch
     out = torch.empty((size, size, nz, 4), dtype=torch.float32, pin_memory=True)
     dev = torch.device("cuda", torch.cuda.current_device())
-    for z in range(nz):
-        g = torch.Generator(device=dev)
-        g.manual_seed(seed * 100003 + ((z0 + z) % size))
-        u = torch.rand((size, size, 2), generator=g, device=dev)
-        cz = 1.0 - 2.0 * u[..., 0]
-        phi = 6.283185307179586 * u[..., 1]
+
+    def s64(c):                                       # 64-bit constant as a signed int64
+        return c - (1 << 64) if c >= (1 << 63) else c
+
+    ax = torch.arange(size, device=dev, dtype=torch.int64)
+    chunk = 64                                        # planes per batch: a handful of launches for the whole slab
+    for c0 in range(0, nz, chunk):
+        zz = (torch.arange(c0, min(nz, c0 + chunk), device=dev, dtype=torch.int64) + z0) % size
+        idx = (ax[:, None, None] * size + ax[None, :, None]) * size + zz[None, None, :]
+        # splitmix64 of (global site index, seed): the value of a site does not depend on who generates it
+        h = idx * s64(0x9E3779B97F4A7C15) + seed
+        h = (h ^ ((h >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
+        h = (h ^ ((h >> 27) & ((1 << 37) - 1))) * s64(0x94D049BB133111EB)
+        h = h ^ ((h >> 31) & ((1 << 33) - 1))
+        u1 = ((h >> 40) & 0xFFFFFF).to(torch.float32) * (1.0 / 16777216.0)
+        u2 = ((h >> 8) & 0xFFFFFF).to(torch.float32) * (1.0 / 16777216.0)
+        cz = 1.0 - 2.0 * u1
+        phi = 6.283185307179586 * u2
         r = torch.sqrt(torch.clamp(1.0 - cz * cz, min=0.0))
-        plane = torch.stack([r * torch.cos(phi), r * torch.sin(phi), cz, torch.ones_like(cz)], -1)
-        out[:, :, z, :].copy_(plane)
+        block = torch.stack([r * torch.cos(phi), r * torch.sin(phi), cz, torch.ones_like(cz)], -1)
+        out[:, :, c0:c0 + block.shape[2], :].copy_(block)
+        del idx, h, u1, u2, cz, phi, r, block
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     return out
 
 
@@ -343,6 +357,12 @@ def run_ours(args):
     achieved_tf = FLOP_PER_ATTEMPT * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e12
     achieved_gbs = BYTES_PER_ATTEMPT * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e9
 
+    traffic = None
+    try:                                              # DRAM bytes per launch from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["bytes_per_launch"] / tj["attempts_per_launch"] * attempts_per_launch
+    except Exception:
+        pass
     if rank == 0:
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         theo = 148 * 128 * 2 * sm_max * 1e6 / 1e12
@@ -360,7 +380,7 @@ def run_ours(args):
                          "attempts_per_launch": attempts_per_launch, "avg_launch_ms": avg_launch_ms,
                          "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                                  "peak_source": hbm_src, "bytes_per_attempt": BYTES_PER_ATTEMPT},
-                         "traffic": None},
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write per launch, scaled by attempts per launch)"},
             "accept_ratio": acc / max(1, acc + rej),
             "wall_s_timed_region": t_wall,
         }
