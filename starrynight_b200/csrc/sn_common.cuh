@@ -36,6 +36,17 @@ __host__ __device__ inline long long sn_pidx(const SnGeom &G, int x, int y, int 
     return ((long long)(x + G.g) * G.PY + (y + G.g)) * G.PZ + (z + G.gz);
 }
 
+// Layout of the tiled kernel's copy: the same padded (x, y) grid, but each z row is stored as 4
+// residue runs: plane z lives at run (z+4)&3, position (z+4)>>2.  A tile's 28-plane window then
+// starts at an aligned position in every run and a TMA row is 7 consecutive float4 (112 B).
+__host__ __device__ inline int sn_q2(const SnGeom &G) { return (G.nz + 8) / 4; }                  // positions per run
+__host__ __device__ inline long long sn_rep_stride2(const SnGeom &G) { return (long long)(G.X + 2 * G.g) * G.PY * 4 * sn_q2(G); }
+__host__ __device__ inline long long sn_pidx2(const SnGeom &G, int x, int y, int z)
+{
+    const int Q = sn_q2(G), zw = z + 4;
+    return (((long long)(x + G.g) * G.PY + (y + G.g)) * 4 + (zw & 3)) * Q + (zw >> 2);
+}
+
 // One colour sublattice per axis.  Period P = cutoff+1; if the extent is not a
 // multiple of P the r = extent % P trailing coordinates get colours of their
 // own, so same-colour sites are always > cutoff apart, also across the wrap.
@@ -123,6 +134,11 @@ struct sn_handle {
     bool species = true;                // false when every length is exactly 1 (skips the l_j multiplies)
     std::vector<char> rep_species;      // per replica: some length != 1
     bool use_tiled = false;
+    // The tiled kernel works on a second copy of the lattice whose z axis is de-interleaved by 4
+    // (layout SnGeom2), so that one TMA row is 7 consecutive float4.  `lat` (canonical) and `lat2` are
+    // synchronised lazily: whoever needs one of them converts from the other if it is stale.
+    float4 *lat2 = nullptr;
+    bool lat_valid = true, lat2_valid = false;
     // slab wiring
     float4 *peer_lat[2] = {nullptr, nullptr};       // lower / upper neighbour's padded lattice
     unsigned int *flags = nullptr;                  // own phase flags (device)
@@ -144,6 +160,7 @@ bool sn_tiled_supported(const sn_handle *h, std::string *why);
 int sn_tiled_prepare(sn_handle *h);
 void sn_tiled_release(sn_handle *h);
 int sn_refresh_ghosts(sn_handle *h);
+int sn_sync_canonical(sn_handle *h);
 int sn_energy_exact_launch(sn_handle *h, int replica, int precision, int n, const int *d_sites,
                            const float *d_newdip, double *d_out);
 int sn_energy_exact_map_launch(sn_handle *h, int replica, int precision, int which, double *d_out);

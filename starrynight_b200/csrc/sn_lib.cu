@@ -225,8 +225,10 @@ extern "C" int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen)
 {
     SN_CHECK_HANDLE(h, replica);
     if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_set_lattice: null buffer");
-    int rc = sn_copy_block(h, replica, const_cast<float *>(xyzlen), true);
+    int rc = sn_sync_canonical(h);                   // other replicas / ghost planes may only live in the tiled copy
     if (rc) return rc;
+    h->lat2_valid = false;
+    if ((rc = sn_copy_block(h, replica, const_cast<float *>(xyzlen), true))) return rc;
     if ((rc = sn_refresh_ghosts(h))) return rc;
     // does any replica carry species (length != 1)?  decides the kernel specialisation
     {
@@ -245,8 +247,9 @@ extern "C" int sn_get_lattice(sn_handle *h, int replica, float *xyzlen)
 {
     SN_CHECK_HANDLE(h, replica);
     if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_get_lattice: null buffer");
-    int rc = sn_copy_block(h, replica, xyzlen, false);
+    int rc = sn_sync_canonical(h);
     if (rc) return rc;
+    if ((rc = sn_copy_block(h, replica, xyzlen, false))) return rc;
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return SN_OK;
 }
@@ -315,6 +318,8 @@ static void sn_launch_colour(const SnSweepArgs &a, int nrep, int cx, int cy, int
 int sn_sweep_colour_launch(sn_handle *h, long long nsweeps, long long *launches)
 {
     const int mode = sn_mode(h);
+    { int rc = sn_sync_canonical(h); if (rc) return rc; }
+    if (nsweeps > 0) h->lat2_valid = false;
     for (long long s = 0; s < nsweeps; s++) {
         SnSweepArgs a = sn_sweep_args(h);
         for (int cx = 0; cx < a.ax.ncol; cx++) for (int cy = 0; cy < a.ay.ncol; cy++) for (int cz = 0; cz < a.az.ncol; cz++) {
@@ -399,6 +404,7 @@ extern "C" int sn_site_energy(sn_handle *h, int replica, int precision, int n, c
     if (n < 0 || (n > 0 && (!sites || !newdip || !dE))) return sn_fail(SN_ERR_INVALID, "sn_site_energy: bad arguments");
     if (precision < SN_PREC_F32 || precision > SN_PREC_REPLICA) return sn_fail(SN_ERR_INVALID, "sn_site_energy: precision %d", precision);
     if (n == 0) return SN_OK;
+    { int rc0 = sn_sync_canonical(h); if (rc0) return rc0; }
     for (int i = 0; i < n; i++)
         if (sites[3 * i] < 0 || sites[3 * i] >= h->G.X || sites[3 * i + 1] < 0 || sites[3 * i + 1] >= h->G.Y || sites[3 * i + 2] < 0 || sites[3 * i + 2] >= h->G.nz)
             return sn_fail(SN_ERR_INVALID, "sn_site_energy: site %d (%d,%d,%d) outside the lattice", i, sites[3 * i], sites[3 * i + 1], sites[3 * i + 2]);
@@ -441,6 +447,7 @@ extern "C" int sn_total_energy(sn_handle *h, int replica, int precision, double 
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
     int rc;
+    if ((rc = sn_sync_canonical(h))) return rc;
     if (precision == SN_PREC_F32) {
         void *s; if ((rc = sn_scratch(h, sizeof(double) * 4 * nblocks, &s))) return rc;
         const float4 *lat = h->lat + (long long)replica * h->G.rep_stride;
@@ -471,7 +478,7 @@ static int sn_dipole_sum(sn_handle *h, int replica, double S[3])
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
     void *s; int rc = sn_scratch(h, sizeof(double) * 3 * nblocks, &s);
-    if (rc) return rc;
+    if (rc || (rc = sn_sync_canonical(h))) return rc;
     sn_sum_dipoles_kernel<<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, (double *)s);
     SN_CUDA_CHECK(cudaGetLastError());
     return sn_reduce_to_host(h, (double *)s, nblocks, 3, S);
@@ -522,7 +529,7 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
     const size_t b_off = off.size() * sizeof(SnRdfOffset), b_first = first.size() * sizeof(int);
     const size_t b_out = sizeof(double) * 2 * SN_RDF_BINS * (size_t)nblocks;
     void *s; int rc = sn_scratch(h, b_out + b_off + b_first + 256, &s);
-    if (rc) return rc;
+    if (rc || (rc = sn_sync_canonical(h))) return rc;
     double *d_out = (double *)s;
     SnRdfOffset *d_off = (SnRdfOffset *)((char *)s + b_out);
     int *d_first = (int *)((char *)s + b_out + ((b_off + 15) / 16) * 16);
@@ -556,7 +563,7 @@ extern "C" int sn_potential_map(sn_handle *h, int replica, double *V)
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     const size_t b_v = sizeof(double) * n, b_off = off.size() * sizeof(SnPotOffset);
     void *s; int rc = sn_scratch(h, b_v + b_off + 64, &s);
-    if (rc) return rc;
+    if (rc || (rc = sn_sync_canonical(h))) return rc;
     double *d_v = (double *)s;
     SnPotOffset *d_off = (SnPotOffset *)((char *)s + ((b_v + 15) / 16) * 16);
     SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));

@@ -63,6 +63,7 @@ extern "C" int sn_get_boundary(sn_handle *h, int replica, int side, float *plane
     SN_CHECK_HANDLE(h, replica);
     if (!planes || side < 0 || side > 1) return sn_fail(SN_ERR_INVALID, "sn_get_boundary: bad arguments");
     if (h->G.gz == 0) return sn_fail(SN_ERR_UNSUPPORTED, "sn_get_boundary: lattice has no interacting Z axis");
+    { int rc = sn_sync_canonical(h); if (rc) return rc; }
     return sn_copy_planes(h, replica, side == 0 ? 0 : h->G.nz - h->G.gz, planes, false);
 }
 
@@ -71,8 +72,10 @@ extern "C" int sn_set_ghost(sn_handle *h, int replica, int side, const float *pl
     SN_CHECK_HANDLE(h, replica);
     if (!planes || side < 0 || side > 1) return sn_fail(SN_ERR_INVALID, "sn_set_ghost: bad arguments");
     if (h->G.periodic_z) return sn_fail(SN_ERR_INVALID, "sn_set_ghost: handle owns the whole Z axis; its ghosts are its own periodic images");
-    int rc = sn_copy_planes(h, replica, side == 0 ? -h->G.gz : h->G.nz, const_cast<float *>(planes), true);
+    int rc = sn_sync_canonical(h);
     if (rc) return rc;
+    h->lat2_valid = false;
+    if ((rc = sn_copy_planes(h, replica, side == 0 ? -h->G.gz : h->G.nz, const_cast<float *>(planes), true))) return rc;
     if ((rc = sn_refresh_ghosts(h))) return rc;      // x / y images of the new planes
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return SN_OK;
@@ -84,7 +87,8 @@ extern "C" int sn_ipc_export(sn_handle *h, void *lattice_handle64, void *flags_h
     if (!lattice_handle64 || !flags_handle64) return sn_fail(SN_ERR_INVALID, "sn_ipc_export: null");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     cudaIpcMemHandle_t a, b;
-    SN_CUDA_CHECK(cudaIpcGetMemHandle(&a, h->lat));
+    // neighbours push into the array the sweep kernel reads: the de-interleaved copy for the tiled kernel
+    SN_CUDA_CHECK(cudaIpcGetMemHandle(&a, h->use_tiled ? h->lat2 : h->lat));
     SN_CUDA_CHECK(cudaIpcGetMemHandle(&b, h->flags));
     memcpy(lattice_handle64, &a, 64); memcpy(flags_handle64, &b, 64);
     return SN_OK;
@@ -124,6 +128,7 @@ extern "C" int sn_attach_peer(sn_handle *h, int side, sn_handle *peer)
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return sn_fail(SN_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
         cudaGetLastError();
     }
-    h->peer_lat[side] = peer->lat; h->peer_flags[side] = peer->flags; h->peer_is_ipc[side] = false;
+    if (peer->use_tiled != h->use_tiled) return sn_fail(SN_ERR_INVALID, "sn_attach_peer: slabs must run the same sweep kernel");
+    h->peer_lat[side] = h->use_tiled ? peer->lat2 : peer->lat; h->peer_flags[side] = peer->flags; h->peer_is_ipc[side] = false;
     return SN_OK;
 }

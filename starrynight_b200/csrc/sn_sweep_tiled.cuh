@@ -215,6 +215,52 @@ __device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], fl
     }
 }
 
+// sn_store_site for the de-interleaved copy (layout sn_pidx2), including the neighbour GPUs' copies
+__device__ __noinline__ void sn_store_images2(float4 *__restrict__ lat2, float4 *__restrict__ peer_lo, float4 *__restrict__ peer_hi,
+                                              const SnGeom &G, int x, int y, int z, const float4 v)
+{
+    const int g = G.g, gz = G.gz;
+    const bool bx = x < g || x >= G.X - g, by = y < g || y >= G.Y - g;
+    const bool bz = z < gz || z >= G.nz - gz;
+    const int kx = bx ? 1 : 0, ky = by ? 1 : 0, kz = (bz && G.periodic_z) ? 1 : 0;     // extents are >= 32 here
+    for (int ix = -kx; ix <= kx; ix++) {
+        const int xi = x + ix * G.X;
+        if (xi < -g || xi >= G.X + g) continue;
+        for (int iy = -ky; iy <= ky; iy++) {
+            const int yi = y + iy * G.Y;
+            if (yi < -g || yi >= G.Y + g) continue;
+            for (int iz = -kz; iz <= kz; iz++) {
+                const int zi = z + iz * G.nz;
+                if (zi < -gz || zi >= G.nz + gz) continue;
+                if (ix | iy | iz) lat2[sn_pidx2(G, xi, yi, zi)] = v;
+            }
+            if (bz && !G.periodic_z) {              // push to the slab neighbours over NVLink
+                if (z < gz && peer_lo) peer_lo[sn_pidx2(G, xi, yi, z + G.nz)] = v;
+                if (z >= G.nz - gz && peer_hi) peer_hi[sn_pidx2(G, xi, yi, z - G.nz)] = v;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void sn_store_site2(float4 *__restrict__ lat2, float4 *__restrict__ peer_lo, float4 *__restrict__ peer_hi,
+                                               const SnGeom &G, int x, int y, int z, const float4 v)
+{
+    lat2[sn_pidx2(G, x, y, z)] = v;
+    const int g = G.g;
+    if (x < g || x >= G.X - g || y < g || y >= G.Y - g || z < G.gz || z >= G.nz - G.gz) sn_store_images2(lat2, peer_lo, peer_hi, G, x, y, z, v);
+}
+
+// canonical padded array <-> de-interleaved copy, every padded cell (ghosts included)
+__global__ void sn_convert_layout_kernel(float4 *__restrict__ lat, float4 *__restrict__ lat2, const SnGeom G, const int to_tiled)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.rep_stride) return;
+    const int zp = (int)(i % G.PZ), yp = (int)((i / G.PZ) % G.PY), xp = (int)(i / ((long long)G.PZ * G.PY));
+    float4 *a = lat + (long long)blockIdx.y * G.rep_stride + i;
+    float4 *b = lat2 + (long long)blockIdx.y * sn_rep_stride2(G) + sn_pidx2(G, xp - G.g, yp - G.g, zp - G.gz);
+    if (to_tiled) *b = *a; else *a = *b;
+}
+
 struct SnTilePhase {
     int px, py, pz;             // tile parity of this launch
     int hx, hy, hz;             // number of active tiles per axis (= tiles / 2)
@@ -270,9 +316,10 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const uint32_t dst = sn_smem_u32(smem) + r * snt::BOX_STRIDE_F4 * 16;
-            // padded coordinates: x0-3 -> x0, y0-3 -> y0, window start z0-4+r -> z0-1+r (ghost width 3)
+            // tensor = (floats of one residue run, run, padded y, padded x, replica); the window of a tile at
+            // z0 starts at position z0/4 of every run, i.e. float z0; halo x0-3 / y0-3 -> padded x0 / y0
             asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                         ::"r"(dst), "l"(&tmap), "r"(0), "r"(z0 - 1 + r), "r"(y0), "r"(x0), "r"(rep), "r"(bar) : "memory");
+                         ::"r"(dst), "l"(&tmap), "r"(z0), "r"(r), "r"(y0), "r"(x0), "r"(rep), "r"(bar) : "memory");
         }
     };
     if (tid == 0 && blockIdx.x < ntiles) issue_tile_load(blockIdx.x);
@@ -286,9 +333,11 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         tm.cage = a.cage; tm.K = a.K; tm.beta = a.beta[rep];
         { const float4 E = a.efield[rep]; tm.E = make_float3(E.x, E.y, E.z); }
         tm.constrain = a.constrain; tm.dim = a.dim;
-        float4 *glat = a.lat + (long long)rep * G.rep_stride;
-        float4 *plo = a.peer_lo ? a.peer_lo + (long long)rep * G.rep_stride : nullptr;
-        float4 *phi = a.peer_hi ? a.peer_hi + (long long)rep * G.rep_stride : nullptr;
+        // a.lat / a.peer_* are the z-de-interleaved copies here (layout sn_pidx2)
+        const long long rs2 = sn_rep_stride2(G);
+        float4 *glat = a.lat + (long long)rep * rs2;
+        float4 *plo = a.peer_lo ? a.peer_lo + (long long)rep * rs2 : nullptr;
+        float4 *phi = a.peer_hi ? a.peer_hi + (long long)rep * rs2 : nullptr;
         const bool face_tile = x0 == 0 || x0 + snt::T == G.X || y0 == 0 || y0 + snt::T == G.Y || z0 == 0 || z0 + snt::T == G.nz;
 
         // Trial orientations for the thread's 2 sites in super-pass sp from ONE Philox4x32-10 call keyed by
@@ -441,12 +490,13 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         }
         // Write the tile's 16^3 interior back: shared memory -> registers, then (once everybody has read) the
         // TMA load of the next tile is started and the registers are stored to global memory underneath it.
-        // Lanes run along z, so a half-warp writes one 256-byte row.  Sites on a lattice / slab face also go
-        // to their ghost images (periodic copies, or the neighbouring GPU's ghost planes over NVLink).
+        // 16 lanes cover one (x,y) row: 4 residue runs x 4 consecutive positions, i.e. four 64-byte pieces
+        // in the de-interleaved global layout.  Sites on a lattice / slab face also go to their ghost
+        // images (periodic copies, or the neighbouring GPU's ghost planes over NVLink).
         {
             float4 wb[16];
-            const int lz = tid & 15, row0 = tid >> 4;
-            const int zo = ((lz + 4) & 3) * snt::BOX_STRIDE_F4 + ((lz + 4) >> 2);
+            const int rr = (tid >> 2) & 3, qq = tid & 3, lz = 4 * qq + rr, row0 = tid >> 4;
+            const int zo = rr * snt::BOX_STRIDE_F4 + qq + 1;              // plane z0 + lz: run rr, window position qq + 1
 #pragma unroll
             for (int pss = 0; pss < 16; pss++) {
                 const int row = pss * 16 + row0, lx = row >> 4, ly = row & 15;
@@ -454,12 +504,13 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             }
             __syncthreads();
             if (tid == 0 && t + gridDim.x < ntiles) issue_tile_load(t + gridDim.x);
-            const long long gbase = sn_pidx(G, x0, y0, z0 + lz);
+            const long long gbase = sn_pidx2(G, x0, y0, z0 + lz);
+            const long long sy2 = 4LL * sn_q2(G), sx2 = sy2 * G.PY;
 #pragma unroll
             for (int pss = 0; pss < 16; pss++) {
                 const int row = pss * 16 + row0, lx = row >> 4, ly = row & 15;
-                if (face_tile) sn_store_site(glat, plo, phi, G, x0 + lx, y0 + ly, z0 + lz, wb[pss]);
-                else glat[gbase + lx * G.sx + ly * G.sy] = wb[pss];
+                if (face_tile) sn_store_site2(glat, plo, phi, G, x0 + lx, y0 + ly, z0 + lz, wb[pss]);
+                else glat[gbase + lx * sx2 + ly * sy2] = wb[pss];
             }
         }
         if (role == 0) {
@@ -502,12 +553,19 @@ int sn_tiled_prepare(sn_handle *h)
     cudaDriverEntryPointQueryResult qr;
     SN_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qr));
     if (!enc || qr != cudaDriverEntryPointSuccess) return sn_fail(SN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    // the de-interleaved copy (layout sn_pidx2) and its tensor map:
+    // dims = (floats of one residue run, 4 runs, padded y, padded x, replica); one TMA row = 7 float4 = 112 B
+    const long long Q = sn_q2(G), rs2 = sn_rep_stride2(G);
+    const size_t bytes2 = (size_t)rs2 * h->p.nreplicas * sizeof(float4);
+    if (cudaMalloc(&h->lat2, bytes2) != cudaSuccess) { cudaGetLastError(); return sn_fail(SN_ERR_NOMEM, "sn_create: cannot allocate %.1f MB for the tiled copy", bytes2 / 1e6); }
+    SN_CUDA_CHECK(cudaMemsetAsync(h->lat2, 0, bytes2, h->stream));
+    h->lat2_valid = false;
     CUtensorMap *tm = new CUtensorMap;
-    const cuuint64_t gdim[5] = {4, (cuuint64_t)G.PZ, (cuuint64_t)G.PY, (cuuint64_t)(G.X + 2 * G.g), (cuuint64_t)h->p.nreplicas};
-    const cuuint64_t gstr[4] = {16, (cuuint64_t)G.PZ * 16, (cuuint64_t)G.sx * 16, (cuuint64_t)G.rep_stride * 16};
-    const cuuint32_t box[5] = {4, 4 * snt::NQ, snt::BX, snt::BX, 1};
-    const cuuint32_t estr[5] = {1, 4, 1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, h->lat, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t gdim[5] = {(cuuint64_t)Q * 4, 4, (cuuint64_t)G.PY, (cuuint64_t)(G.X + 2 * G.g), (cuuint64_t)h->p.nreplicas};
+    const cuuint64_t gstr[4] = {(cuuint64_t)Q * 16, (cuuint64_t)Q * 64, (cuuint64_t)Q * 64 * G.PY, (cuuint64_t)rs2 * 16};
+    const cuuint32_t box[5] = {4 * snt::NQ, 1, snt::BX, snt::BX, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, h->lat2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete tm; return sn_fail(SN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); }
     h->tmap = tm;
@@ -520,6 +578,26 @@ void sn_tiled_release(sn_handle *h)
 {
     delete reinterpret_cast<CUtensorMap *>(h->tmap);
     h->tmap = nullptr;
+    cudaFree(h->lat2);
+    h->lat2 = nullptr;
+}
+
+static int sn_convert_layout(sn_handle *h, bool to_tiled)
+{
+    dim3 grid((unsigned)((h->G.rep_stride + 255) / 256), h->p.nreplicas);
+    sn_convert_layout_kernel<<<grid, 256, 0, h->stream>>>(h->lat, h->lat2, h->G, to_tiled ? 1 : 0);
+    SN_CUDA_CHECK(cudaGetLastError());
+    return SN_OK;
+}
+
+// Bring the canonical array up to date (before anything that reads or partially writes it).
+int sn_sync_canonical(sn_handle *h)
+{
+    if (h->lat_valid) return SN_OK;
+    int rc = sn_convert_layout(h, false);
+    if (rc) return rc;
+    h->lat_valid = true;
+    return SN_OK;
 }
 
 static SnSweepArgs sn_sweep_args(sn_handle *h);
@@ -529,8 +607,17 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
 {
     const SnGeom &G = h->G;
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(h->tmap);
+    if (nsweeps > 0 && !h->lat2_valid) {             // first tiled sweep after the canonical array changed
+        int rc = sn_sync_canonical(h);
+        if (rc || (rc = sn_convert_layout(h, true))) return rc;
+        h->lat2_valid = true;
+    }
+    if (nsweeps > 0) h->lat_valid = false;
+    // Z-slabs: neighbours push into this copy, so nobody may start before everybody's copy is in place
+    if (nsweeps > 0 && !G.periodic_z) { int rc = sn_slab_phase_sync(h, launches); if (rc) return rc; }
     for (long long s = 0; s < nsweeps; s++) {
-        const SnSweepArgs a = sn_sweep_args(h);
+        SnSweepArgs a = sn_sweep_args(h);
+        a.lat = h->lat2;                              // the kernel works on the de-interleaved copies (own and neighbours')
         for (int p = 0; p < 8; p++) {
             SnTilePhase ph;
             ph.px = (p >> 2) & 1; ph.py = (p >> 1) & 1; ph.pz = p & 1;
