@@ -351,7 +351,8 @@ def run_ours(args):
         pass
     hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     fp32_peak = sim.fp32_peak_tflops() if rank == 0 else None
-    sweep_launches = launches if n == 1 else launches // 3       # slab runs add a signal + wait kernel per phase
+    sweep_launches = 8 * spp * args.steps            # one sn_tiled_kernel launch per tile-parity phase; slab runs add
+    #                                                  one signal + one wait kernel per sn_mc_sweeps call (in `launches`)
     avg_launch_ms = ms_local / max(1, sweep_launches)
     attempts_per_launch = (size * size * nz) * spp * args.steps / max(1, sweep_launches)
     achieved_tf = FLOP_PER_ATTEMPT * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e12

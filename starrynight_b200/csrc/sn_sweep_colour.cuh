@@ -59,16 +59,37 @@ __device__ __noinline__ void sn_store_images(float4 *__restrict__ lat, float4 *_
     }
 }
 
-// Write a site and, if it lies within the ghost width of a face, every image of it.
+// Write a site and, if it lies within the ghost width of a face, every image of it.  When every
+// interacting extent is at least twice the ghost width a site has at most one image shift per axis
+// (<= 7 images, a few predicated stores); tiny lattices take the general out-of-line path.
 __device__ __forceinline__ void sn_store_site(float4 *__restrict__ lat, float4 *__restrict__ peer_lo,
                                               float4 *__restrict__ peer_hi, const SnGeom &G,
                                               int x, int y, int z, const float4 v)
 {
     lat[sn_pidx(G, x, y, z)] = v;
     const int g = G.g, gz = G.gz;
-    const bool bx = x < g || x >= G.X - g, by = y < g || y >= G.Y - g;
-    const bool bz = gz > 0 && (z < gz || z >= G.nz - gz);
-    if (bx || by || bz) sn_store_images(lat, peer_lo, peer_hi, G, x, y, z, v);
+    if (G.X < 2 * g || G.Y < 2 * g || (gz > 0 && G.nz < 2 * gz)) {
+        const bool bx = x < g || x >= G.X - g, by = y < g || y >= G.Y - g;
+        const bool bz = gz > 0 && (z < gz || z >= G.nz - gz);
+        if (bx || by || bz) sn_store_images(lat, peer_lo, peer_hi, G, x, y, z, v);
+        return;
+    }
+    const int ix = x < g ? G.X : (x >= G.X - g ? -G.X : 0);
+    const int iy = y < g ? G.Y : (y >= G.Y - g ? -G.Y : 0);
+    const int iz = gz == 0 ? 0 : (z < gz ? G.nz : (z >= G.nz - gz ? -G.nz : 0));
+    if ((ix | iy | iz) == 0) return;
+    if (ix) lat[sn_pidx(G, x + ix, y, z)] = v;
+    if (iy) lat[sn_pidx(G, x, y + iy, z)] = v;
+    if (ix && iy) lat[sn_pidx(G, x + ix, y + iy, z)] = v;
+    if (iz) {
+        float4 *__restrict__ dst = G.periodic_z ? lat : (iz > 0 ? peer_lo : peer_hi);
+        if (dst) {
+            dst[sn_pidx(G, x, y, z + iz)] = v;
+            if (ix) dst[sn_pidx(G, x + ix, y, z + iz)] = v;
+            if (iy) dst[sn_pidx(G, x, y + iy, z + iz)] = v;
+            if (ix && iy) dst[sn_pidx(G, x + ix, y + iy, z + iz)] = v;
+        }
+    }
 }
 
 __device__ __forceinline__ void sn_count(unsigned long long *__restrict__ c, bool attempted, bool accepted, bool vacant)

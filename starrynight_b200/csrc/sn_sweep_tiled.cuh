@@ -215,39 +215,32 @@ __device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], fl
     }
 }
 
-// sn_store_site for the de-interleaved copy (layout sn_pidx2), including the neighbour GPUs' copies
-__device__ __noinline__ void sn_store_images2(float4 *__restrict__ lat2, float4 *__restrict__ peer_lo, float4 *__restrict__ peer_hi,
-                                              const SnGeom &G, int x, int y, int z, const float4 v)
-{
-    const int g = G.g, gz = G.gz;
-    const bool bx = x < g || x >= G.X - g, by = y < g || y >= G.Y - g;
-    const bool bz = z < gz || z >= G.nz - gz;
-    const int kx = bx ? 1 : 0, ky = by ? 1 : 0, kz = (bz && G.periodic_z) ? 1 : 0;     // extents are >= 32 here
-    for (int ix = -kx; ix <= kx; ix++) {
-        const int xi = x + ix * G.X;
-        if (xi < -g || xi >= G.X + g) continue;
-        for (int iy = -ky; iy <= ky; iy++) {
-            const int yi = y + iy * G.Y;
-            if (yi < -g || yi >= G.Y + g) continue;
-            for (int iz = -kz; iz <= kz; iz++) {
-                const int zi = z + iz * G.nz;
-                if (zi < -gz || zi >= G.nz + gz) continue;
-                if (ix | iy | iz) lat2[sn_pidx2(G, xi, yi, zi)] = v;
-            }
-            if (bz && !G.periodic_z) {              // push to the slab neighbours over NVLink
-                if (z < gz && peer_lo) peer_lo[sn_pidx2(G, xi, yi, z + G.nz)] = v;
-                if (z >= G.nz - gz && peer_hi) peer_hi[sn_pidx2(G, xi, yi, z - G.nz)] = v;
-            }
-        }
-    }
-}
-
+// Store a site of the de-interleaved copy (layout sn_pidx2) and, if it lies within the ghost width of a
+// face, its images: the periodic copies in x / y (/ z when the handle owns the whole axis) and the
+// neighbouring GPUs' ghost planes over NVLink.  Extents are >= 32 here, so a site has at most one
+// image shift per axis: at most 7 images, written with a handful of predicated stores.
 __device__ __forceinline__ void sn_store_site2(float4 *__restrict__ lat2, float4 *__restrict__ peer_lo, float4 *__restrict__ peer_hi,
                                                const SnGeom &G, int x, int y, int z, const float4 v)
 {
     lat2[sn_pidx2(G, x, y, z)] = v;
-    const int g = G.g;
-    if (x < g || x >= G.X - g || y < g || y >= G.Y - g || z < G.gz || z >= G.nz - G.gz) sn_store_images2(lat2, peer_lo, peer_hi, G, x, y, z, v);
+    const int g = G.g, gz = G.gz;
+    const int ix = x < g ? G.X : (x >= G.X - g ? -G.X : 0);
+    const int iy = y < g ? G.Y : (y >= G.Y - g ? -G.Y : 0);
+    const int iz = z < gz ? G.nz : (z >= G.nz - gz ? -G.nz : 0);
+    if ((ix | iy | iz) == 0) return;
+    if (ix) lat2[sn_pidx2(G, x + ix, y, z)] = v;
+    if (iy) lat2[sn_pidx2(G, x, y + iy, z)] = v;
+    if (ix && iy) lat2[sn_pidx2(G, x + ix, y + iy, z)] = v;
+    if (iz) {
+        // periodic z: images in this array; Z-slab: the same planes live in the neighbour's ghost shell
+        float4 *__restrict__ dst = G.periodic_z ? lat2 : (iz > 0 ? peer_lo : peer_hi);
+        if (dst) {
+            dst[sn_pidx2(G, x, y, z + iz)] = v;
+            if (ix) dst[sn_pidx2(G, x + ix, y, z + iz)] = v;
+            if (iy) dst[sn_pidx2(G, x, y + iy, z + iz)] = v;
+            if (ix && iy) dst[sn_pidx2(G, x + ix, y + iy, z + iz)] = v;
+        }
+    }
 }
 
 // canonical padded array <-> de-interleaved copy, every padded cell (ghosts included)
@@ -265,6 +258,14 @@ struct SnTilePhase {
     int px, py, pz;             // tile parity of this launch
     int hx, hy, hz;             // number of active tiles per axis (= tiles / 2)
     int nrep;
+    // Z-slab handshake folded into the kernel (all null / 0 for a handle that owns the whole Z axis):
+    // wait until both neighbours have published `wait_epoch` (they finished the previous phase, so my
+    // ghost planes are complete and theirs may be overwritten), and publish `signal_epoch` to them once
+    // the last CTA of this launch has pushed its boundary updates.
+    const unsigned int *flags;          // own flags: [0] written by the lower neighbour, [1] by the upper one
+    unsigned int *to_lower, *to_upper;  // the neighbours' slots for my signal
+    unsigned int *done;                 // CTA arrival counter (device memory, zero between launches)
+    unsigned int wait_epoch, signal_epoch;
 };
 
 template <bool SPECIES>
@@ -290,6 +291,14 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (ph.flags) {                                  // Z-slab: neighbours must have finished the previous phase
+            for (int s = 0; s < 2; s++) {
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ph.flags + s) : "memory");
+                } while ((int)(v - ph.wait_epoch) < 0);
+            }
+        }
     }
     __syncthreads();
 
@@ -528,6 +537,20 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             }
         }
     }
+    if (ph.flags) {
+        // every thread orders its own (peer) stores system-wide; the last CTA to arrive tells the neighbours
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int arrived = atomicAdd(ph.done, 1u);
+            if (arrived == gridDim.x - 1) {
+                *ph.done = 0;
+                __threadfence_system();
+                if (ph.to_lower) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ph.to_lower), "r"(ph.signal_epoch) : "memory");
+                if (ph.to_upper) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ph.to_upper), "r"(ph.signal_epoch) : "memory");
+            }
+        }
+    }
 }
 
 // ---- host side -------------------------------------------------------------------
@@ -624,10 +647,17 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
             ph.hx = G.X / 32; ph.hy = G.Y / 32; ph.hz = G.nz / 32; ph.nrep = h->p.nreplicas;
             const long long ntiles = (long long)ph.hx * ph.hy * ph.hz * ph.nrep;
             const int grid = (int)std::min<long long>(ntiles, h->num_sms);
+            ph.flags = nullptr; ph.to_lower = ph.to_upper = ph.done = nullptr; ph.wait_epoch = ph.signal_epoch = 0;
+            if (!G.periodic_z) {
+                // the phase handshake with the slab neighbours happens inside the kernel: wait for the epoch
+                // published after the previous phase, publish the next one (slots as in sn_slab_phase_sync)
+                ph.flags = h->flags; ph.done = h->flags + 32;
+                ph.to_lower = h->peer_flags[0] + 1; ph.to_upper = h->peer_flags[1] + 0;
+                ph.wait_epoch = h->phase_epoch; ph.signal_epoch = ++h->phase_epoch;
+            }
             if (h->species) sn_tiled_kernel<true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, ph);
             else sn_tiled_kernel<false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, ph);
             if (launches) (*launches)++;
-            if (!G.periodic_z) { int rc = sn_slab_phase_sync(h, launches); if (rc) return rc; }
         }
         h->sweep++;
     }
