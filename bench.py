@@ -276,13 +276,15 @@ def run_ours(args):
     host = synthetic_slab(size, z0, nz)
     host_out = torch.empty_like(host).pin_memory()
 
+    ghosts = None
+    if n > 1:                                        # ghost planes: the neighbours' boundary planes, regenerated locally
+        ghosts = (synthetic_slab(size, (z0 - 3) % size, 3), synthetic_slab(size, (z0 + nz) % size, 3))
+
     def upload():
         sim.set_lattice_ptr(host.data_ptr())
-        if n > 1:                                    # ghost planes: the neighbours' boundary planes, regenerated locally
-            lo = synthetic_slab(size, (z0 - 3) % size, 3)
-            hi = synthetic_slab(size, (z0 + nz) % size, 3)
-            sim.set_ghost(0, lo.numpy())
-            sim.set_ghost(1, hi.numpy())
+        if n > 1:
+            sim.set_ghost(0, ghosts[0].numpy())
+            sim.set_ghost(1, ghosts[1].numpy())
 
     upload()
     if n > 1:                                        # wire the NVLink path: CUDA IPC handles around the ring
@@ -322,14 +324,14 @@ def run_ours(args):
     value = attempts_step * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------
-    h2d = host.numel() * 4
+    h2d = host.numel() * 4 + (sum(g.numel() * 4 for g in ghosts) if ghosts else 0)
     d2h = host_out.numel() * 4 + 24
     for _ in range(min(1, args.warmup)):
-        sim.set_lattice_ptr(host.data_ptr()); sim.MC_sweeps(spp); sim.get_lattice_ptr(host_out.data_ptr())
+        upload(); barrier(); sim.MC_sweeps(spp); sim.get_lattice_ptr(host_out.data_ptr())
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        sim.set_lattice_ptr(host.data_ptr())          # H2D from pinned memory
+        upload()                                      # H2D from pinned memory (slab + its ghost planes)
         if n > 1:
             barrier()                                 # neighbours' uploads done before anyone pushes ghosts
         sim.MC_sweeps(spp)
@@ -351,8 +353,8 @@ def run_ours(args):
         pass
     hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     fp32_peak = sim.fp32_peak_tflops() if rank == 0 else None
-    sweep_launches = 8 * spp * args.steps            # one sn_tiled_kernel launch per tile-parity phase; slab runs add
-    #                                                  one signal + one wait kernel per sn_mc_sweeps call (in `launches`)
+    sweep_launches = args.steps                      # one sn_tiled_kernel launch per sn_mc_sweeps call (all sweeps of a step);
+    #                                                  slab runs add signal + wait kernels around it (in `launches`)
     avg_launch_ms = ms_local / max(1, sweep_launches)
     attempts_per_launch = (size * size * nz) * spp * args.steps / max(1, sweep_launches)
     achieved_tf = FLOP_PER_ATTEMPT * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e12

@@ -59,7 +59,9 @@ typedef enum {
 typedef enum {
     SN_KERNEL_AUTO = 0,    /* tiled shared-memory kernel when the lattice allows it, else colour passes */
     SN_KERNEL_COLOUR = 1,  /* one launch per colour sublattice, neighbours read from global memory */
-    SN_KERNEL_TILED = 2    /* TMA-staged shared-memory tiles (needs cutoff 3, X,Y,nz multiples of 32) */
+    SN_KERNEL_TILED = 2,   /* TMA-staged shared-memory tiles (needs cutoff 3, X,Y,nz multiples of 32) */
+    SN_KERNEL_TILED_PHASED = 3  /* the same kernel, one launch per tile-parity phase instead of one dataflow
+                                   launch per call: validation only, bit-identical results */
 } sn_kernel;
 
 typedef struct {

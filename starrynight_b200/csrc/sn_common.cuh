@@ -18,6 +18,8 @@
 
 #include "../../include/starrynight_b200.h"
 
+#define SN_FLAGS_NEXT 32        // h->flags[32..33]: the tiled kernel's work counter (u64)
+#define SN_FLAGS_VER 64         // h->flags[64..]: tile versions, [rep][X/16][Y/16][nz/16 + 2]
 #define SN_MAX_NB 1024          // neighbour-table capacity in constant memory (cutoff <= 6)
 
 struct SnGeom {
@@ -141,7 +143,7 @@ struct sn_handle {
     bool lat_valid = true, lat2_valid = false;
     // slab wiring
     float4 *peer_lat[2] = {nullptr, nullptr};       // lower / upper neighbour's padded lattice
-    unsigned int *flags = nullptr;                  // own phase flags (device)
+    unsigned int *flags = nullptr;                  // own phase flags [0,1], work counter, tile versions (device; SN_FLAGS_*)
     unsigned int *peer_flags[2] = {nullptr, nullptr};
     unsigned int phase_epoch = 0;
     bool peer_is_ipc[2] = {false, false};

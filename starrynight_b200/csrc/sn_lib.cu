@@ -134,8 +134,15 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
     SN_CUDA_CHECK(cudaMalloc(&h->efield, sizeof(float4) * p->nreplicas));
     SN_CUDA_CHECK(cudaMalloc(&h->counters, sizeof(unsigned long long) * 3 * p->nreplicas));
     SN_CUDA_CHECK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long) * 3 * p->nreplicas, h->stream));
-    SN_CUDA_CHECK(cudaMalloc(&h->flags, sizeof(unsigned int) * 64));
-    SN_CUDA_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(unsigned int) * 64, h->stream));
+    {
+        // phase flags, the tiled kernel's work counter and its tile-version array (one allocation, so that a
+        // slab neighbour reaches all of it through one IPC handle)
+        size_t nflags = SN_FLAGS_VER;
+        if (G.X % 32 == 0 && G.Y % 32 == 0 && G.nz % 32 == 0)
+            nflags += (size_t)p->nreplicas * (G.X / 16) * (G.Y / 16) * (G.nz / 16 + 2);
+        SN_CUDA_CHECK(cudaMalloc(&h->flags, sizeof(unsigned int) * nflags));
+        SN_CUDA_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(unsigned int) * nflags, h->stream));
+    }
     h->h_beta.assign(p->nreplicas, (float)p->beta);
     h->rep_species.assign(p->nreplicas, 0);
     h->species = false;
@@ -153,7 +160,7 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
 
     std::string why;
     const bool can_tile = sn_tiled_supported(h, &why);
-    if (p->kernel == SN_KERNEL_TILED && !can_tile) {
+    if ((p->kernel == SN_KERNEL_TILED || p->kernel == SN_KERNEL_TILED_PHASED) && !can_tile) {
         sn_destroy(h);
         return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: tiled kernel unavailable: %s", why.c_str());
     }

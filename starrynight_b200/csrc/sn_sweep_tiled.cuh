@@ -4,10 +4,21 @@
 // DipoleCutOff = 3 lattices whose X, Y and slab height are multiples of 32.
 //
 // Decomposition
-//   * The lattice is cut into 16^3 tiles.  A sweep is 8 launches ("phases"), one
-//     per tile parity (px,py,pz): active tiles are 32 apart, so the 22^3 read set
-//     of one active tile never meets the 16^3 write set of another.
-//   * One persistent CTA per SM walks the phase's tiles.  Per tile, one thread
+//   * The lattice is cut into 16^3 tiles.  A sweep is 8 "phases", one per tile
+//     parity (px,py,pz): active tiles are 32 apart, so the 22^3 read set of one
+//     active tile never meets the 16^3 write set of another.
+//   * ONE launch runs any number of sweeps as a dataflow over work items
+//     (sweep, phase, tile) taken in that order from a global counter.  There is no
+//     barrier between phases: every tile carries a version (= sweeps it has
+//     completed) and an item starts as soon as its 26 neighbouring tiles have
+//     reached the version that precedes it in the global order (neighbours of an
+//     earlier phase: this sweep done; of a later phase: previous sweep done).
+//     Adjacent tiles are thereby totally ordered -- the result is bit-identical to
+//     8 barrier-separated launches per sweep -- distant tiles run freely and the
+//     phases overlap at their tails.  Z-slab handles see the neighbouring GPUs'
+//     boundary tile layers as ghost entries of the version array, written by the
+//     peers over NVLink, so there is no cross-GPU barrier either.
+//   * One persistent CTA per SM.  Per tile, one thread
 //     issues four cp.async.bulk.tensor (TMA) loads from the padded float4 lattice:
 //     box 22 x 22 x 28(z) with elementStrides = 4 along z, start shifted by the
 //     residue r = 0..3.  Shared memory therefore holds the tile + halo
@@ -53,7 +64,8 @@ constexpr int SITE_THREADS = 128;        // threads of one role; each owns 2 sit
 constexpr int OFF_XF = 4 * BOX_STRIDE_F4 * 16;                 // partial fields handed from role B to role A: float2[2 buffers][3][128]
 constexpr int OFF_XP = OFF_XF + 2 * 3 * SITE_THREADS * 8;      // proposals drawn by role B: float4[2 buffers][2 sites][128]
 constexpr int OFF_BAR = OFF_XP + 2 * 2 * SITE_THREADS * 16;    // mbarrier
-constexpr int SMEM_BYTES = OFF_BAR + 16;
+constexpr int OFF_CTL = OFF_BAR + 16;                          // scheduler hand-over: SnTileItem (48 B) + arrival counter
+constexpr int SMEM_BYTES = OFF_CTL + 64;
 constexpr int THREADS = 256;
 // Column pairs (snt::col numbering) gathered by role A.  Role B works one super-pass ahead of role A's
 // chain, so it may not read a column of the class A is updating: seen from the next class (cx,cy+1)
@@ -254,55 +266,123 @@ __global__ void sn_convert_layout_kernel(float4 *__restrict__ lat, float4 *__res
     if (to_tiled) *b = *a; else *a = *b;
 }
 
-struct SnTilePhase {
-    int px, py, pz;             // tile parity of this launch
-    int hx, hy, hz;             // number of active tiles per axis (= tiles / 2)
+struct SnTileFlow {
+    int hx, hy, hz;                     // active tiles per axis and phase (= tiles / 2)
     int nrep;
-    // Z-slab handshake folded into the kernel (all null / 0 for a handle that owns the whole Z axis):
-    // wait until both neighbours have published `wait_epoch` (they finished the previous phase, so my
-    // ghost planes are complete and theirs may be overwritten), and publish `signal_epoch` to them once
-    // the last CTA of this launch has pushed its boundary updates.
-    const unsigned int *flags;          // own flags: [0] written by the lower neighbour, [1] by the upper one
-    unsigned int *to_lower, *to_upper;  // the neighbours' slots for my signal
-    unsigned int *done;                 // CTA arrival counter (device memory, zero between launches)
-    unsigned int wait_epoch, signal_epoch;
+    unsigned long long base_sweep;      // sweeps completed before item 0 (the version of every tile at that point)
+    unsigned long long n_begin, n_end;  // items of this launch; item n = ((sweep * 8 + phase) * nrep + replica) * hx*hy*hz + tile
+    unsigned long long *next;           // work counter (device, zero at launch): item = n_begin + atomicAdd(next, 1)
+    unsigned int *ver;                  // [rep][2hx][2hy][2hz + 2] tile versions; z index shifted by one ghost layer
+    unsigned int *peer_ver_lo, *peer_ver_hi;   // where my bottom / top tile layer is a ghost layer: the slab neighbours' arrays, or `ver` itself
+    int sys_scope;                      // ghost versions and planes are written by other GPUs
 };
+
+struct __align__(16) SnTileItem {
+    int x0, y0, z0, rep;                // tile origin (slab-local z) and replica
+    int tx, ty, tz, p;                  // tile coordinates and phase (px << 2 | py << 1 | pz)
+    unsigned long long sweep;           // global sweep index = Philox counter word = tile version before the item
+    int valid, ready;                   // (scheduler hand-over) item exists; its dependencies were met when polled
+};
+
+__device__ __forceinline__ SnTileItem sn_tile_item(const SnTileFlow &f, unsigned long long n)
+{
+    SnTileItem it;
+    it.valid = 1; it.ready = 0;
+    const unsigned int P1 = (unsigned int)(f.hx * f.hy * f.hz);
+    const unsigned long long P = (unsigned long long)P1 * f.nrep;
+    const unsigned long long sp = n / P;
+    const unsigned int pos = (unsigned int)(n - sp * P);
+    it.sweep = f.base_sweep + (sp >> 3);
+    it.p = (int)(sp & 7);
+    it.rep = (int)(pos / P1);
+    const int r = (int)(pos % P1), iz = r % f.hz, iy = (r / f.hz) % f.hy;
+    // The x order is rotated by one tile plane per sweep: the wrap-around neighbour (ix - 1 of ix = 0) would
+    // otherwise be the last plane of the previous sweep, i.e. a barrier per sweep; rotated, every dependency
+    // of an item lies at least ~a phase back in the order.
+    const int ix = (r / (f.hz * f.hy) + (int)(it.sweep % (unsigned)f.hx)) % f.hx;
+    it.tx = 2 * ix + ((it.p >> 2) & 1); it.ty = 2 * iy + ((it.p >> 1) & 1); it.tz = 2 * iz + (it.p & 1);
+    it.x0 = it.tx * snt::T; it.y0 = it.ty * snt::T; it.z0 = it.tz * snt::T;
+    return it;
+}
+
+__device__ __forceinline__ long long sn_ver_index(const SnTileFlow &f, int rep, int tx, int ty, int tzg)
+{
+    return (((long long)rep * (2 * f.hx) + tx) * (2 * f.hy) + ty) * (2 * f.hz + 2) + tzg;
+}
+
+// Warp-collective: have the 26 neighbouring tiles of `it` reached the version that precedes it?
+__device__ __forceinline__ bool sn_tile_deps_ready(const SnTileFlow &f, const SnTileItem &it, int lane)
+{
+    bool ok = true;
+    if (lane < 27 && lane != 13) {
+        const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
+        int ntx = it.tx + dx, nty = it.ty + dy;
+        const int ntz = it.tz + dz;                                   // -1 .. 2hz: the ends are ghost layers
+        ntx = ntx < 0 ? ntx + 2 * f.hx : (ntx >= 2 * f.hx ? ntx - 2 * f.hx : ntx);
+        nty = nty < 0 ? nty + 2 * f.hy : (nty >= 2 * f.hy ? nty - 2 * f.hy : nty);
+        const int q = ((ntx & 1) << 2) | ((nty & 1) << 1) | (ntz & 1);
+        const unsigned int need = (unsigned int)it.sweep + (q < it.p ? 1u : 0u);
+        const unsigned int *src = f.ver + sn_ver_index(f, it.rep, ntx, nty, ntz + 1);
+        unsigned int v;
+        if (f.sys_scope) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        ok = (int)(v - need) >= 0;
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
+// One thread, after every store of the tile (write-back, ghost images, pushes to the neighbours) has been fenced.
+__device__ __forceinline__ void sn_tile_publish(const SnTileFlow &f, const SnTileItem &it)
+{
+    const unsigned int v = (unsigned int)it.sweep + 1u;
+    unsigned int *own = f.ver + sn_ver_index(f, it.rep, it.tx, it.ty, it.tz + 1);
+    unsigned int *glo = it.tz == 0 ? f.peer_ver_lo + sn_ver_index(f, it.rep, it.tx, it.ty, 2 * f.hz + 1) : nullptr;
+    unsigned int *ghi = it.tz == 2 * f.hz - 1 ? f.peer_ver_hi + sn_ver_index(f, it.rep, it.tx, it.ty, 0) : nullptr;
+    if (f.sys_scope) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(own), "r"(v) : "memory");
+        if (glo) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(glo), "r"(v) : "memory");
+        if (ghi) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ghi), "r"(v) : "memory");
+    } else {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(own), "r"(v) : "memory");
+        if (glo) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(glo), "r"(v) : "memory");
+        if (ghi) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ghi), "r"(v) : "memory");
+    }
+}
 
 template <bool SPECIES>
 __global__ void __launch_bounds__(snt::THREADS, 1)
-sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, const SnTilePhase ph)
+sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, const SnTileFlow fl)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float4 *tile = reinterpret_cast<float4 *>(smem);
     const uint32_t bar = sn_smem_u32(smem + snt::OFF_BAR);
+    SnTileItem *ctl_item = reinterpret_cast<SnTileItem *>(smem + snt::OFF_CTL);
+    unsigned int *ctl_arrive = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 48);
 
     // Two roles of 128 threads (4 warps) each -- one warp of each role per scheduler, so that one
     // role's issue slots fill the other's latency gaps:
     //   role A gathers column pairs [0, SPLIT) and the own column, then runs the sequential chain;
     //   role B gathers the remaining pairs, hands its partial fields over through shared memory and
-    //          draws the Philox proposals of the next super-pass while A is in the chain.
+    //          draws the Philox proposals of the next super-pass while A is in the chain.  Its first
+    //          warp is also the scheduler: it takes the next work item, polls its dependencies and
+    //          issues the TMA load.
     // thread -> (column i,j ; segment k of 4 z sites ; half h of the segment).  k and the low bit of j
     // vary inside a quarter-warp, so its 8 lanes read 8 distinct 16-byte bank groups (28 j + k mod 8).
     const int tid = threadIdx.x, role = tid >> 7, tl = tid & 127, lane = tid & 31, i = tl >> 5;
     const int k = lane & 3, h = (lane >> 3) & 1, j = ((lane >> 2) & 1) | ((lane >> 4) << 1);
+    const bool sched = (tid >> 5) == 4;
     float2 *xF = reinterpret_cast<float2 *>(smem + snt::OFF_XF);
     float4 *xP = reinterpret_cast<float4 *>(smem + snt::OFF_XP);
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (ph.flags) {                                  // Z-slab: neighbours must have finished the previous phase
-            for (int s = 0; s < 2; s++) {
-                unsigned int v;
-                do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ph.flags + s) : "memory");
-                } while ((int)(v - ph.wait_epoch) < 0);
-            }
-        }
+        *ctl_arrive = 0;
     }
     __syncthreads();
 
-    const long long ntiles = (long long)ph.hx * ph.hy * ph.hz * ph.nrep;
     uint32_t parity = 0;
     const SnGeom &G = a.G;
 
@@ -314,11 +394,8 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         zoff[e] = (w & 3) * snt::BOX_STRIDE_F4 + (w >> 2);
     }
 
-    // TMA load of tile t into shared memory (4 residue boxes), completion on the mbarrier
-    auto issue_tile_load = [&](long long t) {
-        const int iz = (int)(t % ph.hz), iy = (int)((t / ph.hz) % ph.hy), ix = (int)((t / ((long long)ph.hz * ph.hy)) % ph.hx);
-        const int rep = (int)(t / ((long long)ph.hz * ph.hy * ph.hx));
-        const int x0 = (2 * ix + ph.px) * snt::T, y0 = (2 * iy + ph.py) * snt::T, z0 = (2 * iz + ph.pz) * snt::T;
+    // TMA load of a tile into shared memory (4 residue boxes), completion on the mbarrier (one thread)
+    auto issue_tile_load = [&](const SnTileItem &it) {
         // shared memory was last touched through the generic proxy; order it before the async-proxy writes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4 * snt::BOX_BYTES) : "memory");
@@ -328,15 +405,39 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             // tensor = (floats of one residue run, run, padded y, padded x, replica); the window of a tile at
             // z0 starts at position z0/4 of every run, i.e. float z0; halo x0-3 / y0-3 -> padded x0 / y0
             asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                         ::"r"(dst), "l"(&tmap), "r"(z0), "r"(r), "r"(y0), "r"(x0), "r"(rep), "r"(bar) : "memory");
+                         ::"r"(dst), "l"(&tmap), "r"(it.z0), "r"(r), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
         }
     };
-    if (tid == 0 && blockIdx.x < ntiles) issue_tile_load(blockIdx.x);
+    // Scheduler warp.  grab: take the next item number (lane 0; the atomic's latency is left to overlap with
+    // whatever follows).  resolve: decode it, poll its dependencies (spin if `wait`) and hand it to the CTA.
+    auto grab = [&]() -> unsigned long long { return lane == 0 ? fl.n_begin + atomicAdd(fl.next, 1ULL) : 0ULL; };
+    auto deps_met = [&]() {
+        // The halo was written by other CTAs / GPUs through the generic proxy and observed by this warp's
+        // acquire loads; the TMA reads it through the async proxy.
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+    };
+    auto resolve = [&](unsigned long long n_lane0, bool wait) {
+        const unsigned long long n = __shfl_sync(0xffffffffu, n_lane0, 0);
+        SnTileItem it;
+        it.valid = 0; it.ready = 0;
+        if (n < fl.n_end) {
+            it = sn_tile_item(fl, n);
+            bool ready = sn_tile_deps_ready(fl, it, lane);
+            while (wait && !ready) { __nanosleep(100); ready = sn_tile_deps_ready(fl, it, lane); }
+            if (ready) deps_met();
+            it.ready = ready;
+            if (wait && lane == 0) issue_tile_load(it);
+        }
+        if (lane == 0) *ctl_item = it;
+    };
+    unsigned long long pre_n = 0;
+    if (sched) resolve(grab(), true);
+    __syncthreads();
+    SnTileItem item = *ctl_item;
 
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int iz = (int)(t % ph.hz), iy = (int)((t / ph.hz) % ph.hy), ix = (int)((t / ((long long)ph.hz * ph.hy)) % ph.hx);
-        const int rep = (int)(t / ((long long)ph.hz * ph.hy * ph.hx));
-        const int x0 = (2 * ix + ph.px) * snt::T, y0 = (2 * iy + ph.py) * snt::T, z0 = (2 * iz + ph.pz) * snt::T;
+    while (item.valid) {
+        const int x0 = item.x0, y0 = item.y0, z0 = item.z0, rep = item.rep;
+        const uint32_t sweep_lo = (uint32_t)item.sweep, sweep_hi = (uint32_t)(item.sweep >> 32);
 
         SnTerms tm;
         tm.cage = a.cage; tm.K = a.K; tm.beta = a.beta[rep];
@@ -355,7 +456,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             const int gx = x0 + (sp >> 2) + 4 * i, gy = y0 + (sp & 3) + 4 * j, gz = z0 + 4 * k + 2 * h;
             const unsigned long long gsite = ((unsigned long long)gx * G.Y + gy) * G.Z + (G.z0 + gz);
             const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ ((uint32_t)rep << 8),
-                                               a.sweep_lo, a.sweep_hi, a.key0, a.key1);
+                                               sweep_lo, sweep_hi, a.key0, a.key1);
             const uint32_t wa[2] = {r.x, r.z}, wb[2] = {r.y, r.w};
             float4 *dst = xP + (sp & 1) * 2 * snt::SITE_THREADS + tl;
 #pragma unroll
@@ -492,11 +593,15 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 }
             } else if (sp < 15) {
                 // one super-pass ahead of the chain: none of role B's columns belongs to the class being updated
+                if (sp == 14 && sched) pre_n = grab();    // answered by the time the gather below is done
                 gather_b(sp + 1);
                 draw(sp + 1);
+            } else if (sched) {
+                resolve(pre_n, false);                   // role B idles in the last super-pass
             }
             __syncthreads();
         }
+        const SnTileItem nxt = *ctl_item;
         // Write the tile's 16^3 interior back: shared memory -> registers, then (once everybody has read) the
         // TMA load of the next tile is started and the registers are stored to global memory underneath it.
         // 16 lanes cover one (x,y) row: 4 residue runs x 4 consecutive positions, i.e. four 64-byte pieces
@@ -512,7 +617,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 wb[pss] = tile[((lx + snt::H) * snt::BX + (ly + snt::H)) * snt::NQ + zo];
             }
             __syncthreads();
-            if (tid == 0 && t + gridDim.x < ntiles) issue_tile_load(t + gridDim.x);
+            if (sched && lane == 0 && nxt.valid && nxt.ready) issue_tile_load(nxt);
             const long long gbase = sn_pidx2(G, x0, y0, z0 + lz);
             const long long sy2 = 4LL * sn_q2(G), sx2 = sy2 * G.PY;
 #pragma unroll
@@ -521,6 +626,17 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 if (face_tile) sn_store_site2(glat, plo, phi, G, x0 + lx, y0 + ly, z0 + lz, wb[pss]);
                 else glat[gbase + lx * sx2 + ly * sy2] = wb[pss];
             }
+        }
+        // Every lane fences its own stores; the last of the 8 warps to arrive publishes the tile's new version.
+#ifndef SN_EXP_NOFENCE
+        if (fl.sys_scope && (z0 == 0 || z0 + snt::T == G.nz)) __threadfence_system(); else __threadfence();
+#endif
+        __syncwarp();
+        if (lane == 0 && (atomicAdd(ctl_arrive, 1u) & 7u) == 7u) sn_tile_publish(fl, item);
+        if (sched && nxt.valid && !nxt.ready) {
+            while (!sn_tile_deps_ready(fl, nxt, lane)) __nanosleep(100);
+            deps_met();
+            if (lane == 0) issue_tile_load(nxt);
         }
         if (role == 0) {
 #pragma unroll
@@ -536,20 +652,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 if (n_vac) atomicAdd(c + 2, (unsigned long long)n_vac);
             }
         }
-    }
-    if (ph.flags) {
-        // every thread orders its own (peer) stores system-wide; the last CTA to arrive tells the neighbours
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int arrived = atomicAdd(ph.done, 1u);
-            if (arrived == gridDim.x - 1) {
-                *ph.done = 0;
-                __threadfence_system();
-                if (ph.to_lower) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ph.to_lower), "r"(ph.signal_epoch) : "memory");
-                if (ph.to_upper) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ph.to_upper), "r"(ph.signal_epoch) : "memory");
-            }
-        }
+        item = nxt;
     }
 }
 
@@ -630,37 +733,46 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
 {
     const SnGeom &G = h->G;
     const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(h->tmap);
-    if (nsweeps > 0 && !h->lat2_valid) {             // first tiled sweep after the canonical array changed
+    if (nsweeps <= 0) return SN_OK;
+    if (!h->lat2_valid) {                            // first tiled sweep after the canonical array changed
         int rc = sn_sync_canonical(h);
         if (rc || (rc = sn_convert_layout(h, true))) return rc;
         h->lat2_valid = true;
     }
-    if (nsweeps > 0) h->lat_valid = false;
+    h->lat_valid = false;
     // Z-slabs: neighbours push into this copy, so nobody may start before everybody's copy is in place
-    if (nsweeps > 0 && !G.periodic_z) { int rc = sn_slab_phase_sync(h, launches); if (rc) return rc; }
-    for (long long s = 0; s < nsweeps; s++) {
-        SnSweepArgs a = sn_sweep_args(h);
-        a.lat = h->lat2;                              // the kernel works on the de-interleaved copies (own and neighbours')
-        for (int p = 0; p < 8; p++) {
-            SnTilePhase ph;
-            ph.px = (p >> 2) & 1; ph.py = (p >> 1) & 1; ph.pz = p & 1;
-            ph.hx = G.X / 32; ph.hy = G.Y / 32; ph.hz = G.nz / 32; ph.nrep = h->p.nreplicas;
-            const long long ntiles = (long long)ph.hx * ph.hy * ph.hz * ph.nrep;
-            const int grid = (int)std::min<long long>(ntiles, h->num_sms);
-            ph.flags = nullptr; ph.to_lower = ph.to_upper = ph.done = nullptr; ph.wait_epoch = ph.signal_epoch = 0;
-            if (!G.periodic_z) {
-                // the phase handshake with the slab neighbours happens inside the kernel: wait for the epoch
-                // published after the previous phase, publish the next one (slots as in sn_slab_phase_sync)
-                ph.flags = h->flags; ph.done = h->flags + 32;
-                ph.to_lower = h->peer_flags[0] + 1; ph.to_upper = h->peer_flags[1] + 0;
-                ph.wait_epoch = h->phase_epoch; ph.signal_epoch = ++h->phase_epoch;
-            }
-            if (h->species) sn_tiled_kernel<true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, ph);
-            else sn_tiled_kernel<false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, ph);
-            if (launches) (*launches)++;
-        }
-        h->sweep++;
+    if (!G.periodic_z) { int rc = sn_slab_phase_sync(h, launches); if (rc) return rc; }
+
+    SnSweepArgs a = sn_sweep_args(h);
+    a.lat = h->lat2;                                  // the kernel works on the de-interleaved copies (own and neighbours')
+    SnTileFlow f;
+    f.hx = G.X / 32; f.hy = G.Y / 32; f.hz = G.nz / 32; f.nrep = h->p.nreplicas;
+    f.base_sweep = h->sweep;
+    f.next = reinterpret_cast<unsigned long long *>(h->flags + SN_FLAGS_NEXT);
+    f.ver = h->flags + SN_FLAGS_VER;
+    f.peer_ver_lo = G.periodic_z ? f.ver : h->peer_flags[0] + SN_FLAGS_VER;
+    f.peer_ver_hi = G.periodic_z ? f.ver : h->peer_flags[1] + SN_FLAGS_VER;
+    f.sys_scope = !G.periodic_z;
+    const unsigned long long P = (unsigned long long)f.hx * f.hy * f.hz * f.nrep;      // items per phase
+    auto launch = [&](unsigned long long n0, unsigned long long n1) -> int {
+        f.n_begin = n0; f.n_end = n1;
+        SN_CUDA_CHECK(cudaMemsetAsync(f.next, 0, sizeof(unsigned long long), h->stream));
+        const int grid = (int)std::min<unsigned long long>(n1 - n0, (unsigned long long)h->num_sms);
+        if (h->species) sn_tiled_kernel<true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
+        else sn_tiled_kernel<false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
+        if (launches) (*launches)++;
+        return SN_OK;
+    };
+    if (h->p.kernel == SN_KERNEL_TILED_PHASED) {
+        // validation mode: one launch per tile-parity phase (stream order = barrier between phases)
+        for (unsigned long long sp = 0; sp < 8ULL * (unsigned long long)nsweeps; sp++) { int rc = launch(sp * P, (sp + 1) * P); if (rc) return rc; }
+    } else {
+        int rc = launch(0, 8ULL * (unsigned long long)nsweeps * P);
+        if (rc) return rc;
     }
+    h->sweep += (unsigned long long)nsweeps;
     SN_CUDA_CHECK(cudaGetLastError());
+    // Z-slabs: my ghost planes are complete only once both neighbours have finished too
+    if (!G.periodic_z) { int rc = sn_slab_phase_sync(h, launches); if (rc) return rc; }
     return SN_OK;
 }

@@ -20,7 +20,7 @@ def sn(built):
     return starrynight_b200
 
 
-def _run_split(sn, lat, nslab, kernel, sweeps, devices):
+def _run_split(sn, lat, nslab, kernel, sweeps, devices, per_call=1):
     X, Y, Z = lat.shape[:3]
     nz = Z // nslab
     sims = [sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.05, 0, 0), seed=99, device=devices[r % len(devices)], z0=r * nz, nz=nz, kernel=kernel)
@@ -33,9 +33,9 @@ def _run_split(sn, lat, nslab, kernel, sweeps, devices):
         s.set_ghost(1, hi.get_boundary(0))
         s.attach_peer(0, lo)
         s.attach_peer(1, hi)
-    for _ in range(sweeps):                 # one sweep per call per slab: the launch queues never fill
+    for _ in range(sweeps // per_call):     # few sweeps per call per slab: the launch queues never fill
         for s in sims:
-            s.MC_sweeps(1)
+            s.MC_sweeps(per_call)
     out = np.concatenate([s.get_lattice() for s in sims], axis=2)
     counters = np.sum([s.counters() for s in sims], axis=0)
     energy = np.sum([s.total_energy(sn.SN_PREC_F64) for s in sims], axis=0)
@@ -72,3 +72,21 @@ def test_four_slabs_on_two_gpus(sn):
         ref = one.get_lattice()
     out, _, _ = _run_split(sn, lat, 4, sn.SN_KERNEL_TILED, 2, devices=[0, 1])
     assert np.array_equal(out, ref)
+
+
+def test_slabs_run_many_sweeps_per_launch(sn):
+    """Several sweeps in one dataflow launch per slab: the two GPUs are ordered only by the tile versions
+    they publish to each other over NVLink (no launch boundary, no barrier), and the chain is still the
+    single-GPU one bit for bit."""
+    X, Y, Z = 64, 64, 128
+    lat = oa.random_lattice(X, Y, Z, seed=23, lengths=(1.0, 0.5, 0.0), prevalence=(0.8, 0.15, 0.05))
+    with sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.05, 0, 0), seed=99, kernel=sn.SN_KERNEL_TILED_PHASED) as one:
+        one.set_lattice(lat)
+        one.MC_sweeps(6)
+        ref = one.get_lattice()
+        ref_c = np.array(one.counters())
+        ref_e = one.total_energy(sn.SN_PREC_F64)
+    out, counters, energy = _run_split(sn, lat, 2, sn.SN_KERNEL_TILED, 6, devices=[0, 1], per_call=3)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(counters, ref_c)
+    assert np.allclose(energy, ref_e, rtol=1e-12, atol=1e-9)
