@@ -64,9 +64,10 @@ constexpr int SITE_THREADS = 128;        // threads of one role; each owns 2 sit
 constexpr int OFF_XF = 4 * BOX_STRIDE_F4 * 16;                 // partial fields handed from role B to role A: float2[2 buffers][3][128]
 constexpr int OFF_XP = OFF_XF + 2 * 3 * SITE_THREADS * 8;      // proposals drawn by role B: float4[2 buffers][2 sites][128]
 constexpr int OFF_BAR = OFF_XP + 2 * 2 * SITE_THREADS * 16;    // mbarrier
-constexpr int OFF_CTL = OFF_BAR + 16;                          // scheduler hand-over: SnTileItem (48 B) + arrival counter
+constexpr int OFF_CTL = OFF_BAR + 16;                          // control warp hand-over: SnTileItem (48 B) + two arrival counters
 constexpr int SMEM_BYTES = OFF_CTL + 64;
-constexpr int THREADS = 256;
+constexpr int WORKERS = 256;                // 2 roles x 4 warps
+constexpr int THREADS = WORKERS + 32;      // + the control warp
 // Column pairs (snt::col numbering) gathered by role A.  Role B works one super-pass ahead of role A's
 // chain, so it may not read a column of the class A is updating: seen from the next class (cx,cy+1)
 // those are the columns (0,-1), (0,3), and (-1,-1) when cx advances, i.e. pairs 0, 2 and 6.  Pairs 0 and
@@ -324,7 +325,7 @@ __device__ __forceinline__ bool sn_tile_deps_ready(const SnTileFlow &f, const Sn
         const unsigned int need = (unsigned int)it.sweep + (q < it.p ? 1u : 0u);
         const unsigned int *src = f.ver + sn_ver_index(f, it.rep, ntx, nty, ntz + 1);
         unsigned int v;
-        if (f.sys_scope) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        if (f.sys_scope && (ntz < 0 || ntz >= 2 * f.hz)) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
         else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
         ok = (int)(v - need) >= 0;
     }
@@ -338,7 +339,9 @@ __device__ __forceinline__ void sn_tile_publish(const SnTileFlow &f, const SnTil
     unsigned int *own = f.ver + sn_ver_index(f, it.rep, it.tx, it.ty, it.tz + 1);
     unsigned int *glo = it.tz == 0 ? f.peer_ver_lo + sn_ver_index(f, it.rep, it.tx, it.ty, 2 * f.hz + 1) : nullptr;
     unsigned int *ghi = it.tz == 2 * f.hz - 1 ? f.peer_ver_hi + sn_ver_index(f, it.rep, it.tx, it.ty, 0) : nullptr;
-    if (f.sys_scope) {
+    if (f.sys_scope && (glo || ghi)) {
+        // a boundary tile: its pushes into the neighbour GPU's ghost planes (fenced at GPU scope by the
+        // threads that made them, observed here through the arrival counter) become visible system-wide
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(own), "r"(v) : "memory");
         if (glo) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(glo), "r"(v) : "memory");
@@ -359,27 +362,30 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     float4 *tile = reinterpret_cast<float4 *>(smem);
     const uint32_t bar = sn_smem_u32(smem + snt::OFF_BAR);
     SnTileItem *ctl_item = reinterpret_cast<SnTileItem *>(smem + snt::OFF_CTL);
-    unsigned int *ctl_arrive = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 48);
+    unsigned int *ctl_wbread = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 48);   // worker warps that reached the write-back
+    unsigned int *ctl_arrive = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 52);   // worker warps whose stores are fenced
 
     // Two roles of 128 threads (4 warps) each -- one warp of each role per scheduler, so that one
     // role's issue slots fill the other's latency gaps:
     //   role A gathers column pairs [0, SPLIT) and the own column, then runs the sequential chain;
     //   role B gathers the remaining pairs, hands its partial fields over through shared memory and
-    //          draws the Philox proposals of the next super-pass while A is in the chain.  Its first
-    //          warp is also the scheduler: it takes the next work item, polls its dependencies and
-    //          issues the TMA load.
+    //          draws the Philox proposals of the next super-pass while A is in the chain.
+    // A ninth warp is the control warp: it takes the next work item, polls its dependencies, issues the TMA
+    // load as soon as the workers have let go of the shared tile, and publishes the finished tile's version
+    // once their stores have landed -- all the global-memory round trips of the scheduling stay off the
+    // workers' critical path.
     // thread -> (column i,j ; segment k of 4 z sites ; half h of the segment).  k and the low bit of j
     // vary inside a quarter-warp, so its 8 lanes read 8 distinct 16-byte bank groups (28 j + k mod 8).
     const int tid = threadIdx.x, role = tid >> 7, tl = tid & 127, lane = tid & 31, i = tl >> 5;
     const int k = lane & 3, h = (lane >> 3) & 1, j = ((lane >> 2) & 1) | ((lane >> 4) << 1);
-    const bool sched = (tid >> 5) == 4;
+    const bool ctrl = tid >= snt::WORKERS;
     float2 *xF = reinterpret_cast<float2 *>(smem + snt::OFF_XF);
     float4 *xP = reinterpret_cast<float4 *>(smem + snt::OFF_XP);
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        *ctl_arrive = 0;
+        *ctl_arrive = 0; *ctl_wbread = 0;
     }
     __syncthreads();
 
@@ -408,30 +414,57 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                          ::"r"(dst), "l"(&tmap), "r"(it.z0), "r"(r), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
         }
     };
-    // Scheduler warp.  grab: take the next item number (lane 0; the atomic's latency is left to overlap with
-    // whatever follows).  resolve: decode it, poll its dependencies (spin if `wait`) and hand it to the CTA.
-    auto grab = [&]() -> unsigned long long { return lane == 0 ? fl.n_begin + atomicAdd(fl.next, 1ULL) : 0ULL; };
+    // ---- control warp -----------------------------------------------------------------------------
     auto deps_met = [&]() {
         // The halo was written by other CTAs / GPUs through the generic proxy and observed by this warp's
         // acquire loads; the TMA reads it through the async proxy.
         asm volatile("fence.proxy.async.global;" ::: "memory");
     };
-    auto resolve = [&](unsigned long long n_lane0, bool wait) {
-        const unsigned long long n = __shfl_sync(0xffffffffu, n_lane0, 0);
+    auto take = [&]() -> SnTileItem {
+        unsigned long long n = lane == 0 ? fl.n_begin + atomicAdd(fl.next, 1ULL) : 0ULL;
+        n = __shfl_sync(0xffffffffu, n, 0);
         SnTileItem it;
         it.valid = 0; it.ready = 0;
-        if (n < fl.n_end) {
-            it = sn_tile_item(fl, n);
-            bool ready = sn_tile_deps_ready(fl, it, lane);
-            while (wait && !ready) { __nanosleep(100); ready = sn_tile_deps_ready(fl, it, lane); }
-            if (ready) deps_met();
-            it.ready = ready;
-            if (wait && lane == 0) issue_tile_load(it);
-        }
-        if (lane == 0) *ctl_item = it;
+        if (n < fl.n_end) it = sn_tile_item(fl, n);
+        return it;
     };
-    unsigned long long pre_n = 0;
-    if (sched) resolve(grab(), true);
+    if (ctrl) {
+        SnTileItem cur = take();
+        if (cur.valid) {
+            while (!sn_tile_deps_ready(fl, cur, lane)) __nanosleep(100);
+            deps_met();
+            if (lane == 0) issue_tile_load(cur);
+        }
+        if (lane == 0) *ctl_item = cur;
+        __syncthreads();
+        for (unsigned int done = 8; cur.valid; done += 8) {
+            // while the workers compute `cur`: next item, first look at its dependencies
+            SnTileItem nxt = take();
+            bool ready = false;
+            while (*reinterpret_cast<volatile unsigned int *>(ctl_wbread) + 8u - done == 0u) {     // no worker warp at the write-back yet
+                if (nxt.valid && !ready) ready = sn_tile_deps_ready(fl, nxt, lane);
+                else __nanosleep(100);
+            }
+            if (ready) deps_met();
+            nxt.ready = ready;
+            if (lane == 0) *ctl_item = nxt;
+            __syncthreads();                              // hand-over: every worker has read its part of the tile
+            if (ready && lane == 0) issue_tile_load(nxt);
+            while ((int)(*reinterpret_cast<volatile unsigned int *>(ctl_arrive) - done) < 0) __nanosleep(40);
+            __syncwarp();
+            if (lane == 0) sn_tile_publish(fl, cur);
+            if (nxt.valid && !ready) {
+                while (!sn_tile_deps_ready(fl, nxt, lane)) __nanosleep(100);
+                deps_met();
+                if (lane == 0) issue_tile_load(nxt);
+            }
+            cur = nxt;
+        }
+        return;
+    }
+
+    // ---- workers -----------------------------------------------------------------------------------
+    auto workers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(snt::WORKERS) : "memory"); };
     __syncthreads();
     SnTileItem item = *ctl_item;
 
@@ -491,7 +524,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             dst[2 * snt::SITE_THREADS] = make_float2(F[1].y, F[1].z);
         };
         if (role == 1) gather_b(0);
-        __syncthreads();
+        workers_sync();
 
         int n_acc = 0, n_rej = 0, n_vac = 0;
 #pragma unroll 1
@@ -593,20 +626,17 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 }
             } else if (sp < 15) {
                 // one super-pass ahead of the chain: none of role B's columns belongs to the class being updated
-                if (sp == 14 && sched) pre_n = grab();    // answered by the time the gather below is done
                 gather_b(sp + 1);
                 draw(sp + 1);
-            } else if (sched) {
-                resolve(pre_n, false);                   // role B idles in the last super-pass
             }
-            __syncthreads();
+            workers_sync();
         }
-        const SnTileItem nxt = *ctl_item;
         // Write the tile's 16^3 interior back: shared memory -> registers, then (once everybody has read) the
         // TMA load of the next tile is started and the registers are stored to global memory underneath it.
         // 16 lanes cover one (x,y) row: 4 residue runs x 4 consecutive positions, i.e. four 64-byte pieces
         // in the de-interleaved global layout.  Sites on a lattice / slab face also go to their ghost
         // images (periodic copies, or the neighbouring GPU's ghost planes over NVLink).
+        SnTileItem nxt;
         {
             float4 wb[16];
             const int rr = (tid >> 2) & 3, qq = tid & 3, lz = 4 * qq + rr, row0 = tid >> 4;
@@ -616,8 +646,10 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 const int row = pss * 16 + row0, lx = row >> 4, ly = row & 15;
                 wb[pss] = tile[((lx + snt::H) * snt::BX + (ly + snt::H)) * snt::NQ + zo];
             }
-            __syncthreads();
-            if (sched && lane == 0 && nxt.valid && nxt.ready) issue_tile_load(nxt);
+            __syncwarp();
+            if (lane == 0) atomicAdd(ctl_wbread, 1u);     // tells the control warp to stop polling and come to the hand-over
+            __syncthreads();                              // hand-over: the control warp starts the next TMA load
+            nxt = *ctl_item;
             const long long gbase = sn_pidx2(G, x0, y0, z0 + lz);
             const long long sy2 = 4LL * sn_q2(G), sx2 = sy2 * G.PY;
 #pragma unroll
@@ -627,17 +659,13 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 else glat[gbase + lx * sx2 + ly * sy2] = wb[pss];
             }
         }
-        // Every lane fences its own stores; the last of the 8 warps to arrive publishes the tile's new version.
+        // Every lane fences its own stores (GPU scope); the control warp sees the 8 arrivals, makes boundary
+        // pushes visible system-wide and publishes the tile's new version.
 #ifndef SN_EXP_NOFENCE
-        if (fl.sys_scope && (z0 == 0 || z0 + snt::T == G.nz)) __threadfence_system(); else __threadfence();
+        __threadfence();
 #endif
         __syncwarp();
-        if (lane == 0 && (atomicAdd(ctl_arrive, 1u) & 7u) == 7u) sn_tile_publish(fl, item);
-        if (sched && nxt.valid && !nxt.ready) {
-            while (!sn_tile_deps_ready(fl, nxt, lane)) __nanosleep(100);
-            deps_met();
-            if (lane == 0) issue_tile_load(nxt);
-        }
+        if (lane == 0) atomicAdd(ctl_arrive, 1u);
         if (role == 0) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
