@@ -22,8 +22,8 @@
  *   Hysteresis : { amplitude = 0.1; steps = 64; cycles = 1; }   triangular Efield.x ramp after
  *                       equilibration (the loop main.c:229-238 only has commented out); prints
  *                       "T: %d Efield: x %f Polar: %f" per field point (main.c:82)
- * Terminal art (outputlattice_dumb_terminal) and the recombination model are not part of the
- * accelerated path and are reported as skipped.
+ * Terminal art (outputlattice_dumb_terminal, the ANSI density plots of recombination_calculator) is
+ * not reproduced; the numbers those routines print are.
  *
  *   --init-only FILE    build the initial lattice exactly as the run would, write it as raw
  *                       float[X][Y][Z][4] to FILE and exit before touching the GPU (used by tests).
@@ -234,6 +234,32 @@ static void do_rdf(sn_handle *h, const char *fn)
     write_rdf(fn, fe, afe, cnt);
 }
 
+static void write_efield_xyz(sn_handle *h, const char *fn, int cutoff, int half_offset)   /* analysis.c:379-389, 468-479 */
+{
+    FILE *fo; int x, y, z;
+    SN(sn_efield_map(h, 0, cutoff, half_offset, Vbuf));
+    fo = fopen(fn, "w");
+    if (!fo) { perror(fn); return; }
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++) fprintf(fo, "%d %d %d %f\n", x, y, z, Vbuf[site(x, y, z)]);
+    fclose(fo);
+}
+
+static void do_recombination(sn_handle *h, FILE *log)                      /* analysis.c:96-228 */
+{
+    double r[SN_RECOMB_N];
+    SN(sn_recombination(h, 0, r));
+    if (log) {
+        fprintf(log, "T: %d ZBe: %e ZBh: %e ZFDe: %e ZFDh: %e R_Boltz: %e ", T, r[0], r[1], r[2], r[3], r[4]);
+        fprintf(log, "R_FD: %e FD-Total-electron: %e FD-Total-hole: %e\n", r[5], r[6], r[7]);
+        fflush(log);
+    }
+    {                                                                      /* the echo below the density plots, :224-227 */
+        fprintf(stderr, "Density eMAX: %f hMAX: %f\nRMAX: %e\n", r[8], r[9], r[10]);
+        fprintf(stderr, "T: %d ZBe: %e ZBh: %e ZFDe: %e ZFDh: %e R_Boltz: %e \n", T, r[0], r[1], r[2], r[3], r[4]);
+        fprintf(stderr, "R_FD: %e FD-Total-electron: %e FD-Total-hole: %e\n", r[5], r[6], r[7]);
+    }
+}
+
 static void terminal_summary(void)
 {
     /* the last line outputlattice_dumb_terminal prints (analysis.c:923-925), from the z = 0 slice of V */
@@ -245,7 +271,8 @@ static void terminal_summary(void)
 static void analysis_initial(sn_handle *h)                                 /* main.c:29-48 */
 {
     int need_v = CalculatePotential || SavePotentialCube || DisplayDumbTerminal;
-    if (CalculateEfield) fprintf(stderr, "CalculateEfield: E-field maps are outside the accelerated path, skipped\n");
+    if (CalculateEfield) write_efield_xyz(h, "initial_lattice_efield.xyz", 4, 0);          /* main.c:31-32 */
+    if (CalculateEfield) write_efield_xyz(h, "initial_lattice_efieldoffset.xyz", 2, 1);
     if (need_v) refresh_potential(h);
     if (CalculatePotential) write_potential_xyz("initial_lattice_potential.xyz", Vbuf);
     if (SavePotentialCube) write_potential_cube("initial_lattice_potential.cube", Vbuf);
@@ -256,18 +283,22 @@ static void analysis_initial(sn_handle *h)                                 /* ma
     if (CalculateRadialOrderParameter) do_rdf(h, "rdf.dat");
     if (SaveDipolesPNG) write_lattice_ppm_hsv("initial.png", latbuf);
     if (DisplayDumbTerminal) terminal_summary();
-    if (CalculateRecombination) fprintf(stderr, "CalculateRecombination: the recombination model is outside the accelerated path, skipped\n");
+    if (CalculateRecombination) do_recombination(h, stderr);                                /* main.c:47 */
 }
 
-static void analysis_midpoint(sn_handle *h, int MCstep)                    /* main.c:51-103 */
+static void analysis_midpoint(sn_handle *h, int MCstep, FILE *log)         /* main.c:51-103 */
 {
     char name[160], prefix[100];
     int need_v = CalculatePotential || SavePotentialCube || DisplayDumbTerminal;
     sprintf(prefix, "T_%04d_%d_%03d", T, (int)CageStrain, MCstep);       /* main.c:58 */
     if (need_v) refresh_potential(h);
     if (DisplayDumbTerminal) terminal_summary();
+    if (CalculateRecombination) do_recombination(h, log);                                   /* main.c:73 */
     sprintf(name, "%s-RDF.dat", prefix);
     if (CalculateRadialOrderParameter) do_rdf(h, name);
+    sprintf(name, "%s_efield.xyz", prefix);
+    if (CalculateEfield) write_efield_xyz(h, name, 4, 0);                                   /* main.c:85-86; reuses Vbuf */
+    if (CalculateEfield && need_v) refresh_potential(h);
     sprintf(name, "%s_potential.xyz", prefix);
     if (CalculatePotential) write_potential_xyz(name, Vbuf);
     sprintf(name, "%s_potential.cube", prefix);
@@ -359,6 +390,7 @@ int main(int argc, char *argv[])
     fprintf(stderr, "Equilibriation MC moves... %e\n", (double)sweeps_per_megastep * (double)nsites * (double)MCEqmSteps);
     for (i = 0; i < MCEqmSteps; i++) { fprintf(stderr, ","); SN(sn_mc_sweeps(h, sweeps_per_megastep)); }   /* main.c:219-223 */
     SN(sn_synchronize(h));
+    if (CalculateEfield) write_efield_xyz(h, "equilib_lattice_efield.xyz", 4, 0);           /* main.c:225 */
     if (CalculatePotential) { refresh_potential(h); write_potential_png("equilib_pot.png", Vbuf); }
     if (SaveDipolesSVG) { SN(sn_get_lattice(h, 0, latbuf)); write_lattice_svg("equilib-SVG.svg", latbuf); }
 
@@ -383,7 +415,7 @@ int main(int argc, char *argv[])
         SN(sn_mc_sweeps(h, sweeps_per_megastep));
         SN(sn_synchronize(h));
         toc = now_s();
-        analysis_midpoint(h, i);
+        analysis_midpoint(h, i, log);
         fflush(stdout);
         tac = now_s();
         fprintf(stderr, "MC Moves (per second): %f MHz\n", 1e-6 * (double)sweeps_per_megastep * (double)nsites / (toc - tic));

@@ -151,6 +151,14 @@ SN_API int sn_landau_order(sn_handle *h, int replica, double *landau);
 SN_API int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum, long long *count);
 /* replaces dipole_potential() over the lattice (analysis.c:65-94,264-308): V[X][Y][nz] */
 SN_API int sn_potential_map(sn_handle *h, int replica, double *V);
+/* replaces dipole_electricfield(cutoff, x, y, z) over the lattice (analysis.c:393-479, lattice_Efield_XYZ uses
+ * cutoff 4) and, with half_offset != 0, dipole_electricfieldoffset (analysis.c:310-389, cutoff 2): |E| per site,
+ * Emag[X][Y][nz] */
+SN_API int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_offset, double *Emag);
+/* replaces the physics of recombination_calculator() (analysis.c:96-170): out = ZBe ZBh ZFDe ZFDh R_Boltz R_FD
+ * FD-Total-electron FD-Total-hole eMAX hMAX RMAX */
+#define SN_RECOMB_N 11
+SN_API int sn_recombination(sn_handle *h, int replica, double out[SN_RECOMB_N]);
 
 /* measurement aid for bench.py: sustained FFMA throughput of `device` in TFLOP/s, the
  * denominator of the FP32 CUDA-core roofline (MEASURED_PEAKS.json carries no FP32 figure) */

@@ -68,7 +68,7 @@ class Oracle:
         self.lib.sno_mt_int32.restype = C.c_ulong
         self.lib.sno_mt_real1.restype = C.c_double
         self.lib.sno_mt_real2.restype = C.c_double
-        for name in ("polarisation", "landau_order", "dipole_potential"):
+        for name in ("polarisation", "landau_order", "dipole_potential", "dipole_electricfield"):
             getattr(self.lib, f"sno_{name}_{prec}").restype = C.c_double
 
     def fn(self, name):
@@ -148,6 +148,19 @@ class Oracle:
         self.fn("potential_map")(C.byref(p), _ptr(lat, self.ct), _ptr(out, C.c_double))
         return out
 
+    def efield_map(self, p, lat, cutoff=4, half_offset=False):
+        lat = self._lat(lat)
+        out = np.zeros(p.X * p.Y * p.Z, np.float64)
+        self.fn("efield_map")(C.byref(p), _ptr(lat, self.ct), int(cutoff), int(half_offset), _ptr(out, C.c_double))
+        return out
+
+    def recombination(self, p, lat):
+        """ZBe ZBh ZFDe ZFDh R_Boltz R_FD e_total h_total eMAX hMAX RMAX (analysis.c:96-170)."""
+        lat = self._lat(lat)
+        out = np.zeros(11, np.float64)
+        self.fn("recombination")(C.byref(p), _ptr(lat, self.ct), _ptr(out, C.c_double))
+        return out
+
     def rdf(self, p, lat):
         """Accumulated (fe_sum, afe_sum, count) for r^2 = 0..80, before division."""
         lat = self._lat(lat)
@@ -184,8 +197,10 @@ class RefLib:
         L.ref_seed.argtypes = [C.c_ulong]
         L.ref_mc_moves.argtypes = [C.c_int]
         L.ref_genrand_int32.restype = C.c_ulong
-        for n in ("ref_genrand_real1", "ref_genrand_real2", "ref_polarisation", "ref_landau_order", "ref_dipole_potential"):
+        for n in ("ref_genrand_real1", "ref_genrand_real2", "ref_polarisation", "ref_landau_order", "ref_dipole_potential",
+                  "ref_dipole_electricfield"):
             getattr(L, n).restype = C.c_double
+        L.ref_dipole_electricfield.argtypes = [C.c_int] * 4
         L.ref_dipole_potential.argtypes = [C.c_int] * 3
         self.p = None
 
@@ -280,6 +295,16 @@ class RefLib:
 
     def rdf_file(self, path):
         self.lib.ref_radial_order_parameter(path.encode())
+
+    def efield_map(self, cutoff=4, half_offset=False):
+        out = np.zeros(self.n, np.float64)
+        self.lib.ref_efield_map(int(cutoff), int(half_offset), _ptr(out, C.c_double))
+        return out
+
+    def recombination_log(self, path):
+        """The two lines recombination_calculator writes to its log (analysis.c:129-131,169-171)."""
+        self.lib.ref_recombination(path.encode())
+        return open(path).read()
 
 
 def random_lattice(X, Y, Z, seed=0, lengths=(1.0,), prevalence=(1.0,), dtype=np.float32):

@@ -175,6 +175,27 @@ REF_API void ref_potential_map(double *v)
     int x, y, z; size_t i = 0;
     for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++, i++) v[i] = dipole_potential(x, y, z);
 }
+/* dipole_electricfield / dipole_electricfieldoffset (analysis.c:310-465).  The offset variant
+ * prints every term to stderr (analysis.c:361-368): the caller silences stderr around it. */
+REF_API double ref_dipole_electricfield(int cutoff, int x, int y, int z) { return dipole_electricfield(cutoff, x, y, z); }
+REF_API void ref_efield_map(int cutoff, int half_offset, double *v)
+{
+    int x, y, z; size_t i = 0;
+    FILE *saved = stderr;
+    if (half_offset) stderr = fopen("/dev/null", "w");
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++, i++)
+        v[i] = half_offset ? dipole_electricfieldoffset(cutoff, x, y, z) : dipole_electricfield(cutoff, x, y, z);
+    if (half_offset) { fclose(stderr); stderr = saved; }
+}
+/* recombination_calculator (analysis.c:96-228): the two log lines go to `logfile`, the terminal art to /dev/null */
+REF_API void ref_recombination(const char *logfile)
+{
+    FILE *log = fopen(logfile, "w"), *saved = stderr;
+    stderr = fopen("/dev/null", "w");
+    recombination_calculator(log);
+    fclose(stderr); stderr = saved;
+    fclose(log);
+}
 /* appends one block to `filename` exactly as the reference does (analysis.c:528) */
 REF_API void ref_radial_order_parameter(const char *filename) { radial_order_parameter((char *)filename); }
 REF_API void ref_lattice_potential_XYZ(const char *filename) { lattice_potential_XYZ((char *)filename); }

@@ -39,6 +39,7 @@ typedef struct {
 typedef struct { unsigned long mt[624]; int left; int next; } sno_mt;
 
 #define SNO_MAXNB 10000   /* montecarlo-core.c:29 */
+#define SNO_RECOMB_N 11   /* ZBe ZBh ZFDe ZFDh R_Boltz R_FD e_total h_total eMAX hMAX RMAX (analysis.c:96-228) */
 #define SNO_RDF_BINS 81   /* analysis.c:540-550: bins 0..80 are zeroed and printed */
 
 /* MT19937 (mt19937ar-cok.c:63-196): published Matsumoto-Nishimura algorithm */
@@ -66,7 +67,12 @@ int sno_gen_neighbours(const sno_params *p, int *dxyz, double *d);
     double sno_landau_order_##SUF(const sno_params *p, const REAL *lat);                            \
     double sno_dipole_potential_##SUF(const sno_params *p, const REAL *lat, int x, int y, int z);   \
     void sno_potential_map_##SUF(const sno_params *p, const REAL *lat, double *v);                  \
-    void sno_rdf_##SUF(const sno_params *p, const REAL *lat, REAL *fe, REAL *afe, int *count);
+    void sno_rdf_##SUF(const sno_params *p, const REAL *lat, REAL *fe, REAL *afe, int *count);      \
+    double sno_dipole_electricfield_##SUF(const sno_params *p, const REAL *lat, int cutoff,         \
+                                          int half_offset, int x, int y, int z);                    \
+    void sno_efield_map_##SUF(const sno_params *p, const REAL *lat, int cutoff, int half_offset,    \
+                              double *v);                                                           \
+    void sno_recombination_##SUF(const sno_params *p, const REAL *lat, double out[SNO_RECOMB_N]);
 
 SNO_DECL(f32, float)
 SNO_DECL(f64, double)

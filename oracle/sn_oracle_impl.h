@@ -279,4 +279,80 @@ void FN(sno_rdf)(const sno_params *p, const REAL *lat, REAL *fe, REAL *afe, int 
         }
 }
 
+/* analysis.c:393-465 (dipole_electricfield: integer offsets, self term excluded, -p_i/3 added at the end)
+ * and :310-376 (dipole_electricfieldoffset: the field half a lattice step off the sites, offsets
+ * dx + 0.5 for dx in [-CUTOFF-1, CUTOFF-1], nothing excluded).  Species lengths are NOT applied there.
+ * Statement order and types as written: r, n, the contribution and the running field are `struct dipole`
+ * members (REAL), `radial` is a double, `3*n.x*radial - p.x` is evaluated in double and narrowed. */
+double FN(sno_dipole_electricfield)(const sno_params *p, const REAL *lat, int CUTOFF, int half, int x, int y, int z)
+{
+    int dx, dy, dz; const int X = p->X, Y = p->Y, Z = p->Z;
+    REAL E[3], c[3], r[3], n[3], d; double radial;
+    const int lo = half ? -CUTOFF - 1 : -CUTOFF, hi = half ? CUTOFF - 1 : CUTOFF;
+    E[0] = 0.0; E[1] = 0.0; E[2] = 0.0;
+    for (dx = lo; dx <= hi; dx++) for (dy = lo; dy <= hi; dy++) for (dz = lo; dz <= hi; dz++) {
+        const REAL *t;
+        if (!half && dx == 0 && dy == 0 && dz == 0) continue;                /* :411 */
+        if (half) { r[0] = (REAL)(dx) + 0.5; r[1] = (REAL)(dy) + 0.5; r[2] = (REAL)(dz) + 0.5; }   /* :330 */
+        else { r[0] = (REAL)(dx); r[1] = (REAL)(dy); r[2] = (REAL)(dz); }    /* :414 */
+        d = sqrt((REAL)r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);             /* :416 */
+        if (d > (REAL)CUTOFF) continue;                                       /* :418 */
+        n[0] = r[0] / d; n[1] = r[1] / d; n[2] = r[2] / d;                    /* :426 */
+        t = lat + IDX(p, (X + x + dx) % X, (Y + y + dy) % Y, (Z + z + dz) % Z);
+        radial = FN(dot3)(n, t);                                              /* :429 */
+        c[0] = 3 * n[0] * radial - t[0];                                      /* :432-434 */
+        c[1] = 3 * n[1] * radial - t[1];
+        c[2] = 3 * n[2] * radial - t[2];
+        c[0] /= d * d * d; c[1] /= d * d * d; c[2] /= d * d * d;              /* :437-439 */
+        E[0] += c[0]; E[1] += c[1]; E[2] += c[2];                             /* :442-444 */
+    }
+    if (!half) {                                                              /* :457-459 */
+        const REAL *s = lat + IDX(p, x, y, z);
+        E[0] -= 1 / 3.0 * s[0]; E[1] -= 1 / 3.0 * s[1]; E[2] -= 1 / 3.0 * s[2];
+    }
+    return sqrt(FN(dot3)(E, E));                                              /* :464 */
+}
+
+void FN(sno_efield_map)(const sno_params *p, const REAL *lat, int cutoff, int half, double *v)
+{
+    int x, y, z; size_t i = 0;
+    for (x = 0; x < p->X; x++) for (y = 0; y < p->Y; y++) for (z = 0; z < p->Z; z++, i++)
+        v[i] = FN(sno_dipole_electricfield)(p, lat, cutoff, half, x, y, z);
+}
+
+/* analysis.c:96-170, the physics of recombination_calculator: Boltzmann and Fermi-Dirac partition sums
+ * of the screened dipole potential, then the e/h densities and their overlap.  out = ZBe ZBh ZFDe ZFDh
+ * R_Boltz R_FD electron_total hole_total eMAX hMAX RMAX (the maxima are over the z = 0 plane, :157-159).
+ * R_Boltz is (X*Y*Z)*(X*Y*Z)/(ZBe*ZBh) with the product taken in int there (:131; wraps beyond 215^2
+ * sites); here it is taken in double. */
+void FN(sno_recombination)(const sno_params *p, const REAL *lat, double out[SNO_RECOMB_N])
+{
+    int x, y, z; const int X = p->X, Y = p->Y, Z = p->Z; const double N = (double)X * Y * Z;
+    double BETA = 1 / (0.025), potentialeV = 0.165, pot;                      /* :104-106 */
+    double ZBe = 0.0, ZBh = 0.0, ZFDe = 0.0, ZFDh = 0.0, et = 0.0, ht = 0.0, rt = 0.0, eMAX = 0.0, hMAX = 0.0, RMAX = 0.0;
+    double *V = (double *)malloc(sizeof(double) * (size_t)N);
+    size_t i = 0;
+    potentialeV /= 5;
+    FN(sno_potential_map)(p, lat, V);
+    for (i = 0; i < (size_t)N; i++) {                                         /* :112-127 */
+        pot = potentialeV * V[i];
+        ZBe += exp(-pot * BETA); ZBh += exp(pot * BETA);
+        ZFDe += 1.0 / (exp(pot * BETA) + 1.0); ZFDh += 1.0 / (exp(-pot * BETA) + 1.0);
+    }
+    for (x = 0, i = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++, i++) {   /* :140-166 */
+        double e, h, e0, h0, pot0;
+        pot = potentialeV * V[i];
+        e = 1.0 / (exp(pot * BETA) + 1.0) / ZFDe; h = 1.0 / (exp(-pot * BETA) + 1.0) / ZFDh;
+        pot0 = potentialeV * V[i - (size_t)z];
+        e0 = 1.0 / (exp(pot0 * BETA) + 1.0) / ZFDe; h0 = 1.0 / (exp(-pot0 * BETA) + 1.0) / ZFDh;
+        if (e0 > eMAX) eMAX = e0;
+        if (h0 > hMAX) hMAX = h0;
+        if (e0 * h0 > RMAX) RMAX = e0 * h0;
+        et += e; ht += h; rt += e * h;
+    }
+    out[0] = ZBe; out[1] = ZBh; out[2] = ZFDe; out[3] = ZFDh; out[4] = N * N / (ZBe * ZBh);
+    out[5] = N * rt; out[6] = et; out[7] = ht; out[8] = eMAX; out[9] = hMAX; out[10] = RMAX;
+    free(V);
+}
+
 #undef IDX

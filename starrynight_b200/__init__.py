@@ -29,7 +29,7 @@ EXPORTS = [
     "sn_last_error", "sn_version", "sn_default_params", "sn_create", "sn_destroy", "sn_neighbour_table",
     "sn_set_lattice", "sn_get_lattice", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_mc_sweeps",
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_site_energy",
-    "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_get_boundary",
+    "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_get_boundary",
     "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak",
 ]
 
@@ -80,6 +80,8 @@ def load_library() -> C.CDLL:
     lib.sn_landau_order.argtypes = [H, C.c_int, C.POINTER(C.c_double)]
     lib.sn_rdf.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sn_potential_map.argtypes = [H, C.c_int, C.c_void_p]
+    lib.sn_efield_map.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.sn_recombination.argtypes = [H, C.c_int, C.c_void_p]
     lib.sn_get_boundary.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.sn_set_ghost.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.sn_ipc_export.argtypes = [H, C.c_void_p, C.c_void_p]
@@ -249,6 +251,18 @@ class Simulation:
         v = np.zeros(self.nsites, np.float64)
         _check(self.lib.sn_potential_map(self.h, replica, v.ctypes.data))
         return v.reshape(self.X, self.Y, self.nz)
+
+    def dipole_electricfield(self, cutoff=4, half_offset=False, replica=0):
+        """|E| per site: dipole_electricfield / dipole_electricfieldoffset (analysis.c:310-465)."""
+        v = np.zeros(self.nsites, np.float64)
+        _check(self.lib.sn_efield_map(self.h, replica, int(cutoff), int(half_offset), v.ctypes.data))
+        return v.reshape(self.X, self.Y, self.nz)
+
+    def recombination(self, replica=0):
+        """recombination_calculator (analysis.c:96-170): ZBe ZBh ZFDe ZFDh R_Boltz R_FD e_total h_total eMAX hMAX RMAX."""
+        v = np.zeros(11, np.float64)
+        _check(self.lib.sn_recombination(self.h, replica, v.ctypes.data))
+        return v
 
     # -- Z-slab plumbing
     def get_boundary(self, side, replica=0):

@@ -553,11 +553,9 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
     return SN_OK;
 }
 
-extern "C" int sn_potential_map(sn_handle *h, int replica, double *V)
+// potential map into device scratch (first n doubles of *scratch); extra_bytes are reserved behind it
+static int sn_potential_device(sn_handle *h, int replica, size_t extra_bytes, double **d_v, void **extra)
 {
-    SN_CHECK_HANDLE(h, replica);
-    if (!V) return sn_fail(SN_ERR_INVALID, "sn_potential_map: null");
-    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_potential_map: not available on a Z-slab handle (radius-6 halo)");
     const int MAXR = 6;                             // analysis.c:68
     std::vector<SnPotOffset> off;
     for (int dx = -MAXR; dx <= MAXR; dx++) for (int dy = -MAXR; dy <= MAXR; dy++) for (int dz = -MAXR; dz <= MAXR; dz++) {
@@ -568,16 +566,92 @@ extern "C" int sn_potential_map(sn_handle *h, int replica, double *V)
         off.push_back(o);
     }
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
-    const size_t b_v = sizeof(double) * n, b_off = off.size() * sizeof(SnPotOffset);
+    const size_t b_v = ((sizeof(double) * n + 15) / 16) * 16, b_off = ((off.size() * sizeof(SnPotOffset) + 15) / 16) * 16;
+    void *s; int rc = sn_scratch(h, b_v + b_off + extra_bytes + 64, &s);
+    if (rc || (rc = sn_sync_canonical(h))) return rc;
+    *d_v = (double *)s;
+    SnPotOffset *d_off = (SnPotOffset *)((char *)s + b_v);
+    if (extra) *extra = (char *)s + b_v + b_off;
+    SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(SnPotOffset), cudaMemcpyHostToDevice, h->stream));
+    sn_potential_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), *d_v);
+    SN_CUDA_CHECK(cudaGetLastError());
+    return SN_OK;
+}
+
+extern "C" int sn_potential_map(sn_handle *h, int replica, double *V)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!V) return sn_fail(SN_ERR_INVALID, "sn_potential_map: null");
+    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_potential_map: not available on a Z-slab handle (radius-6 halo)");
+    double *d_v; int rc = sn_potential_device(h, replica, 0, &d_v, nullptr);
+    if (rc) return rc;
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    SN_CUDA_CHECK(cudaMemcpyAsync(V, d_v, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_offset, double *Emag)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!Emag) return sn_fail(SN_ERR_INVALID, "sn_efield_map: null");
+    if (cutoff < 1 || cutoff > 8) return sn_fail(SN_ERR_INVALID, "sn_efield_map: cutoff %d outside 1..8", cutoff);
+    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_efield_map: not available on a Z-slab handle (halo wider than the ghost shell)");
+    // offsets as the reference walks them: integer steps without the origin (analysis.c:407-418), or
+    // dx + 0.5 for dx in [-cutoff-1, cutoff-1] (analysis.c:322-334); d <= cutoff
+    const int lo = half_offset ? -cutoff - 1 : -cutoff, hi = half_offset ? cutoff - 1 : cutoff;
+    std::vector<SnEfOffset> off;
+    for (int dx = lo; dx <= hi; dx++) for (int dy = lo; dy <= hi; dy++) for (int dz = lo; dz <= hi; dz++) {
+        if (!half_offset && !dx && !dy && !dz) continue;
+        const double sh = half_offset ? 0.5 : 0.0, rx = dx + sh, ry = dy + sh, rz = dz + sh;
+        const double d = sqrt(rx * rx + ry * ry + rz * rz);
+        if (d > (double)cutoff) continue;
+        SnEfOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.pad = 0;
+        o.nx = rx / d; o.ny = ry / d; o.nz = rz / d; o.w = 1.0 / (d * d * d);
+        off.push_back(o);
+    }
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const size_t b_v = ((sizeof(double) * n + 15) / 16) * 16, b_off = off.size() * sizeof(SnEfOffset);
     void *s; int rc = sn_scratch(h, b_v + b_off + 64, &s);
     if (rc || (rc = sn_sync_canonical(h))) return rc;
     double *d_v = (double *)s;
-    SnPotOffset *d_off = (SnPotOffset *)((char *)s + ((b_v + 15) / 16) * 16);
+    SnEfOffset *d_off = (SnEfOffset *)((char *)s + b_v);
     SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));
-    sn_potential_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), d_v);
+    sn_efield_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(),
+                                                                          half_offset ? 0 : 1, d_v);
     SN_CUDA_CHECK(cudaGetLastError());
-    SN_CUDA_CHECK(cudaMemcpyAsync(V, d_v, b_v, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaMemcpyAsync(Emag, d_v, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
+}
+
+extern "C" int sn_recombination(sn_handle *h, int replica, double out[SN_RECOMB_N])
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!out) return sn_fail(SN_ERR_INVALID, "sn_recombination: null");
+    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_recombination: not available on a Z-slab handle (radius-6 halo)");
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
+    double *d_v; void *extra;
+    int rc = sn_potential_device(h, replica, sizeof(double) * 8 * nblocks, &d_v, &extra);
+    if (rc) return rc;
+    const double BETA = 1 / (0.025), potentialeV = 0.165 / 5;                 // analysis.c:104-106
+    sn_recombination_kernel<<<nblocks, 256, 0, h->stream>>>(d_v, n, h->G.nz, potentialeV * BETA, (double *)extra);
+    SN_CUDA_CHECK(cudaGetLastError());
+    std::vector<double> hp((size_t)nblocks * 8);
+    SN_CUDA_CHECK(cudaMemcpyAsync(hp.data(), extra, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    double sum[5] = {0, 0, 0, 0, 0}, mx[3] = {0, 0, 0};
+    for (int b = 0; b < nblocks; b++) {
+        for (int k = 0; k < 5; k++) sum[k] += hp[(size_t)b * 8 + k];
+        for (int k = 0; k < 3; k++) mx[k] = std::max(mx[k], hp[(size_t)b * 8 + 5 + k]);
+    }
+    const double ZBe = sum[0], ZBh = sum[1], ZFDe = sum[2], ZFDh = sum[3], N = (double)n;
+    out[0] = ZBe; out[1] = ZBh; out[2] = ZFDe; out[3] = ZFDh;
+    out[4] = N * N / (ZBe * ZBh);                                             // R_Boltz (:131; in double, the reference's int product wraps)
+    out[5] = N * sum[4] / (ZFDe * ZFDh);                                      // R_FD = N * sum e_i h_i (:169)
+    out[6] = sum[2] / ZFDe; out[7] = sum[3] / ZFDh;                            // FD totals (:163-164)
+    out[8] = mx[0] / ZFDe; out[9] = mx[1] / ZFDh; out[10] = mx[2] / (ZFDe * ZFDh);   // maxima over z = 0 (:157-159)
     return SN_OK;
 }
 

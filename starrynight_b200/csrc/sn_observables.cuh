@@ -5,6 +5,9 @@
 //   landau_order()            :506-526   |sum_i p_i|^2                   -> same sums, finished on the host
 //   radial_order_parameter()  :528-598   FE / AFE correlations by r^2    -> sn_rdf_kernel
 //   dipole_potential()        :65-94     V_i = sum_j l_j p_j.r / d^3     -> sn_potential_kernel
+//   dipole_electricfield()    :393-465   |E_i|, E_i = sum_j (3 n n.p_j - p_j)/d^3 - p_i/3  -> sn_efield_kernel
+//   dipole_electricfieldoffset() :310-376  the same half a lattice step off the sites    -> sn_efield_kernel
+//   recombination_calculator():96-170    Boltzmann / Fermi-Dirac partition sums of V     -> sn_recombination_kernel
 // and the lattice energy the reference never finished (main.c:63)        -> sn_energy_f32_kernel.
 // Accumulation is FP64 (int64 for counts): the reference's float sums and int
 // counts stop being sound beyond ~128^3.
@@ -184,4 +187,66 @@ __global__ void __launch_bounds__(128) sn_potential_kernel(const float4 *__restr
         pot += (double)c.w * ((double)c.x * f.dx + (double)c.y * f.dy + (double)c.z * f.dz) * f.w;
     }
     V[i] = pot;
+}
+
+// ---- dipole electric-field maps (analysis.c:310-376, 393-465) -------------------
+struct SnEfOffset { short dx, dy, dz, pad; double nx, ny, nz, w; };   // n = r/d, w = 1/d^3
+
+__global__ void __launch_bounds__(128) sn_efield_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnEfOffset *__restrict__ off,
+                                                        int noff, int self_term, double *__restrict__ Emag)
+{
+    const long long n = (long long)G.X * G.Y * G.nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x, y, z; sn_site_of(G, i, x, y, z);
+    double ex = 0.0, ey = 0.0, ez = 0.0;
+    for (int o = 0; o < noff; o++) {
+        const SnEfOffset f = off[o];
+        int xx = (x + f.dx) % G.X, yy = (y + f.dy) % G.Y, zz = (z + f.dz) % G.nz;
+        if (xx < 0) xx += G.X;
+        if (yy < 0) yy += G.Y;
+        if (zz < 0) zz += G.nz;
+        const float4 c = lat[sn_pidx(G, xx, yy, zz)];
+        const double radial = f.nx * c.x + f.ny * c.y + f.nz * c.z;           // species length not applied (analysis.c:429-434)
+        ex += (3.0 * f.nx * radial - c.x) * f.w;
+        ey += (3.0 * f.ny * radial - c.y) * f.w;
+        ez += (3.0 * f.nz * radial - c.z) * f.w;
+    }
+    if (self_term) {                                                          // analysis.c:457-459
+        const float4 c = lat[sn_pidx(G, x, y, z)];
+        ex -= c.x / 3.0; ey -= c.y / 3.0; ez -= c.z / 3.0;
+    }
+    Emag[i] = sqrt(ex * ex + ey * ey + ez * ez);
+}
+
+// ---- recombination model (analysis.c:96-170) ------------------------------------
+// One pass over the potential map: partial sums of exp(-bV), exp(bV), f_e = 1/(exp(bV)+1), f_h = 1/(exp(-bV)+1)
+// and f_e f_h, and the maxima of f_e, f_h, f_e f_h over the z = 0 plane -> out[block][8].  The
+// normalisations by Z_FDe, Z_FDh are applied on the host.
+__global__ void __launch_bounds__(256) sn_recombination_kernel(const double *__restrict__ V, long long n, int nz, double scale,
+                                                               double *__restrict__ out)
+{
+    __shared__ double sm[5 * 8];
+    __shared__ double smax[3 * 8];
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, m[3] = {0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double a = scale * V[i];                                        // pot * BETA
+        const double ep = exp(a), em = exp(-a);
+        const double fe = 1.0 / (ep + 1.0), fh = 1.0 / (em + 1.0);
+        v[0] += em; v[1] += ep; v[2] += fe; v[3] += fh; v[4] += fe * fh;
+        if (i % nz == 0) { m[0] = fmax(m[0], fe); m[1] = fmax(m[1], fh); m[2] = fmax(m[2], fe * fh); }
+    }
+    sn_block_sum<5, 256>(v, sm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[k] = fmax(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+        if (lane == 0) smax[k * 8 + warp] = m[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 5; k++) out[8 * blockIdx.x + k] = v[k];
+        for (int k = 0; k < 3; k++) { double t = 0.0; for (int w = 0; w < 8; w++) t = fmax(t, smax[k * 8 + w]); out[8 * blockIdx.x + 5 + k] = t; }
+    }
 }

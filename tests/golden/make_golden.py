@@ -35,8 +35,41 @@ def parse_rdf(path):
     return np.array([[float(v) for v in r] for r in rows])
 
 
+def case_inputs(name):
+    X, Y, Z, cut, cage, K, E, beta, lens, prev, constrain, dim = CASES[name]
+    E = tuple(float(np.float32(v)) for v in E)
+    p = oa.make_params(X, Y, Z, cut, cage, K, E, beta, constrain, dim, 300)
+    lat = oa.random_lattice(X, Y, Z, seed=sum(map(ord, name)), lengths=lens, prevalence=prev)
+    return p, lat
+
+
+def make_extra(refs):
+    """analysis_extra.npz: dipole_electricfield (cutoff 4), dipole_electricfieldoffset (cutoff 2) maps and the
+    two log lines of recombination_calculator, from the reference build, on the lattices of the cases above
+    (same inputs: regenerated from the case name, checked against the stored lattice by the tests)."""
+    out = {}
+    for name in ("species3d", "flat2d", "odd_cut2", "cut4_constrain", "dim2"):
+        p, lat = case_inputs(name)
+        for prec, r in refs.items():
+            r.configure(p)
+            r.set_lattice(lat)
+            out[f"{name}_efield_{prec}"] = r.efield_map(4, False)
+            out[f"{name}_efieldoffset_{prec}"] = r.efield_map(2, True)
+            with tempfile.NamedTemporaryFile(suffix=".log", delete=False) as f:
+                path = f.name
+            txt = r.recombination_log(path)
+            os.unlink(path)
+            out[f"{name}_recombination_{prec}"] = np.frombuffer(txt.encode(), np.uint8)
+        print(name, txt.strip()[:100])
+    np.savez_compressed(os.path.join(HERE, "analysis_extra.npz"), **out)
+
+
 def main():
     refs = {prec: oa.RefLib(prec) for prec in ("f32", "f64")}
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        make_extra(refs)
+        return
+    make_extra(refs)
     for name, (X, Y, Z, cut, cage, K, E, beta, lens, prev, constrain, dim) in CASES.items():
         E = tuple(float(np.float32(v)) for v in E)   # Efield is a float in the reference and in the C ABI
         p = oa.make_params(X, Y, Z, cut, cage, K, E, beta, constrain, dim, 300)

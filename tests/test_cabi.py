@@ -18,7 +18,7 @@ def declared_symbols():
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for must in ("sn_create", "sn_destroy", "sn_set_lattice", "sn_get_lattice", "sn_mc_sweeps", "sn_site_energy",
-                 "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map",
+                 "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination",
                  "sn_get_counters", "sn_ipc_export", "sn_ipc_attach"):
         assert must in syms
 

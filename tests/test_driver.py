@@ -94,3 +94,37 @@ def test_driver_run_writes_the_reference_files(built, tmp_path):
     # production step files: same names, same shapes
     assert len((tmp_path / "T_0300_1_000_potential.xyz").read_text().splitlines()) == 20 * 20 * 28
     assert len(_floats((tmp_path / "T_0300_1_000-RDF.dat").read_text(), 0)) == len(_floats(ref["T_0300_1_000-RDF.dat"].decode(), 0))
+
+
+@pytest.mark.gpu
+def test_driver_efield_maps_and_recombination_log(built, tmp_path):
+    """CalculateEfield / CalculateRecombination (main.c:31-32,47,73,85-86,225): same files, same line formats,
+    numbers equal to the reference's routines on the same initial lattice."""
+    from oracle import oracle_api as oa
+    from tests.test_oracle import parse_recombination_log
+    cfg = ref_files()["starrynight.cfg"].decode()
+    cfg = cfg.replace("X=20", "X=12").replace("Y=20", "Y=10").replace("Z=28", "Z=12")
+    cfg = cfg.replace("CalculateEfield: false", "CalculateEfield: true").replace("CalculateRecombination: false", "CalculateRecombination: true")
+    if "CalculateEfield: true" not in cfg:
+        cfg += "\nCalculateEfield: true\n"
+    if "CalculateRecombination: true" not in cfg:
+        cfg += "\nCalculateRecombination: true\n"
+    cfg = cfg.replace("MCMegaSteps: 20", "MCMegaSteps: 2").replace("MCEqmSteps: 5", "MCEqmSteps: 1").replace("MCMoves: 200.0", "MCMoves: 2.0")
+    (tmp_path / "starrynight.cfg").write_text(cfg)
+    run = subprocess.run([DRIVER], cwd=tmp_path, capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-2000:]
+    lat0 = run_init_only(tmp_path, cfg).reshape(12, 10, 12, 4)
+    p = oa.make_params(12, 10, 12)
+    o = oa.Oracle("f64")
+    for fn, cut, half in (("initial_lattice_efield.xyz", 4, False), ("initial_lattice_efieldoffset.xyz", 2, True)):
+        txt = (tmp_path / fn).read_text()
+        assert len(txt.splitlines()) == 12 * 10 * 12
+        assert np.max(np.abs(_floats(txt, 3) - o.efield_map(p, lat0, cut, half))) < 1e-6        # %f
+    for fn in ("equilib_lattice_efield.xyz", "T_0300_1_000_efield.xyz", "T_0300_1_001_efield.xyz"):
+        assert len((tmp_path / fn).read_text().splitlines()) == 12 * 10 * 12
+    # initial recombination numbers go to stderr (main.c:47), one line per production mega-step to the log (:73)
+    first = [l for l in run.stderr.splitlines() if l.startswith("T: 300 ZBe:") and "R_FD:" in l][0]
+    assert np.allclose(parse_recombination_log(first), o.recombination(p, lat0)[:8], rtol=1.5e-6)
+    log = (tmp_path / "Recombination_T_0300.log").read_text().splitlines()
+    rows = [l for l in log if l.startswith("T: 300 ZBe:")]
+    assert len(rows) == 2 and all("R_FD:" in l and "FD-Total-hole:" in l for l in rows)

@@ -69,3 +69,25 @@ def test_large_lattice_properties(sn):
         assert cnt[1] == 6 * X ** 3 and cnt[74] == 120 * X ** 3          # int64 counts: beyond int32 at 512^3
         e = sim.total_energy(sn.SN_PREC_F64)
         assert e[1] == pytest.approx(-3.0 * X ** 3, rel=1e-13)
+
+
+@pytest.mark.parametrize("name", ["species3d", "flat2d", "odd_cut2", "cut4_constrain", "dim2"])
+def test_efield_maps_and_recombination_against_golden(sn, name):
+    """sn_efield_map / sn_recombination (FP64 kernels) against the reference build's vectors:
+    1e-12 of the float->double build, float accuracy of the native one."""
+    from tests.test_oracle import parse_recombination_log
+    from tests.helpers import GOLDEN
+    g, p = load_case(name)
+    x = dict(np.load(f"{GOLDEN}/analysis_extra.npz"))
+    lat = g["lattice"]
+    with sim_for(sn, p, lat) as sim:
+        for key, cut, half in (("efield", 4, False), ("efieldoffset", 2, True)):
+            E = sim.dipole_electricfield(cut, half).ravel()                  # analysis.c:310-465
+            ref = x[f"{name}_{key}_f64"]
+            assert np.max(np.abs(E - ref)) < 1e-12 * np.max(np.abs(ref)) * 50
+            assert np.max(np.abs(E - x[f"{name}_{key}_f32"])) < 2e-5 * np.max(np.abs(ref))
+        got = sim.recombination()                                            # analysis.c:96-171
+    ref = parse_recombination_log(bytes(x[f"{name}_recombination_f64"]).decode())
+    assert np.allclose(got[:8], ref, rtol=1.5e-6)                            # the log holds 7 digits
+    full = oa.Oracle("f64").recombination(p, lat)
+    assert np.allclose(got, full, rtol=1e-11)

@@ -127,3 +127,30 @@ def test_oracle_vs_reference_build_fresh_inputs(built, prec):
     assert np.array_equal(o.potential_map(p, lo), r.potential_map())
     assert o.polarisation(p, lo) == r.polarisation()
     assert o.landau_order(p, lo) == r.landau_order()
+
+
+RECOMB_KEYS = ["ZBe", "ZBh", "ZFDe", "ZFDh", "R_Boltz", "R_FD", "FD-Total-electron", "FD-Total-hole"]
+EXTRA_CASES = ["species3d", "flat2d", "odd_cut2", "cut4_constrain", "dim2"]
+
+
+def parse_recombination_log(txt):
+    """`T: %d ZBe: %e ... R_Boltz: %e R_FD: %e FD-Total-electron: %e FD-Total-hole: %e` (analysis.c:129-131,169-171)."""
+    import re
+    return np.array([float(re.search(re.escape(k) + r":\s*(\S+)", txt).group(1)) for k in RECOMB_KEYS])
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", EXTRA_CASES)
+def test_efield_maps_and_recombination_match_golden(built, name, prec):
+    """dipole_electricfield / dipole_electricfieldoffset (analysis.c:310-465) bit for bit, and the numbers
+    recombination_calculator logs (analysis.c:96-171) to the 7 digits it prints."""
+    g, p = load_case(name)
+    x = dict(np.load(f"{GOLDEN}/analysis_extra.npz"))
+    o = oa.Oracle(prec)
+    lat = g["lattice"]
+    assert np.array_equal(o.efield_map(p, lat, 4, False), x[f"{name}_efield_{prec}"])
+    assert np.array_equal(o.efield_map(p, lat, 2, True), x[f"{name}_efieldoffset_{prec}"])
+    ref = parse_recombination_log(bytes(x[f"{name}_recombination_{prec}"]).decode())
+    got = o.recombination(p, lat)
+    assert np.allclose(got[:8], ref, rtol=1.5e-6)
+    assert got[6] == pytest.approx(1.0, abs=1e-12) and got[7] == pytest.approx(1.0, abs=1e-12)   # densities are normalised
