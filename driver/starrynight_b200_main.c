@@ -19,6 +19,11 @@
  *   Seed (int)          Philox / MT seed instead of 0xDEADBEEF + T
  *   Device (int)        CUDA device ordinal
  *   Kernel (string)     "auto" | "colour" | "tiled"
+ *   GPUs (int)          Z-slab decomposition over this many GPUs of the box (devices Device, Device+1, ...):
+ *                       one slab handle per GPU, boundary updates pushed GPU-to-GPU over NVLink by the sweep
+ *                       kernels; the chain is bit-identical to the single-GPU one.  Z must be a multiple of
+ *                       GPUs x 4 (GPUs x 32 for the tiled kernel).  The lattice-wide analysis (potential,
+ *                       RDF, E-field, recombination: halos of 6-9 sites) runs on a full copy on the first GPU.
  *   Hysteresis : { amplitude = 0.1; steps = 64; cycles = 1; }   triangular Efield.x ramp after
  *                       equilibration (the loop main.c:229-238 only has commented out); prints
  *                       "T: %d Efield: x %f Polar: %f" per field point (main.c:82)
@@ -49,7 +54,7 @@ static const char *InitialLattice = "random";
 static float dip_length[10], dip_prevalence[10];
 static int dipolecount = 0;
 static long long seed_override = -1;
-static int device = 0, kernel = SN_KERNEL_AUTO;
+static int device = 0, kernel = SN_KERNEL_AUTO, ngpus = 1;
 static double hyst_amplitude = 0.0;
 static int hyst_steps = 0, hyst_cycles = 1;
 
@@ -108,6 +113,8 @@ static void load_config(const char *path)
     /* optional B200 keys */
     if (snc_lookup_int(&cfg, "Seed", &i)) seed_override = (unsigned int)i;
     snc_lookup_int(&cfg, "Device", &device);
+    snc_lookup_int(&cfg, "GPUs", &ngpus);
+    if (ngpus < 1 || ngpus > 16) { fprintf(stderr, "GPUs = %d outside 1..16\n", ngpus); exit(EXIT_FAILURE); }
     if (snc_lookup_string(&cfg, "Kernel", &str))
         kernel = !strcmp(str, "colour") ? SN_KERNEL_COLOUR : !strcmp(str, "tiled") ? SN_KERNEL_TILED : SN_KERNEL_AUTO;
     snc_lookup_float(&cfg, "Hysteresis.amplitude", &hyst_amplitude);
@@ -225,6 +232,95 @@ static void write_lattice_ppm_hsv(const char *fn, const float *lat)       /* ana
 static double *Vbuf;
 static float *latbuf;
 
+/* ---- the sweep engine: one handle, or GPUs slab handles + a full-lattice analysis handle ---- */
+static sn_handle *slab[16];
+static float *slabbuf;
+static int analysis_stale = 0;
+
+static void slab_planes(const float *lat, float *dst, int zfirst, int nplanes)   /* planes zfirst.. (periodic) of lat[X][Y][Z][4] */
+{
+    int x, y, k;
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (k = 0; k < nplanes; k++)
+        memcpy(dst + (((size_t)x * Y + y) * nplanes + k) * 4, lat + site(x, y, ((zfirst + k) % Z + Z) % Z) * 4, 4 * sizeof(float));
+}
+
+static void slabs_create(const sn_params *base, const float *lat)
+{
+    int r; const int nz = Z / ngpus, g = DipoleCutOff;
+    float *ghost = (float *)malloc((size_t)X * Y * g * 4 * sizeof(float));
+    slabbuf = (float *)malloc((size_t)X * Y * nz * 4 * sizeof(float));
+    if (Z % ngpus || !ghost || !slabbuf) { fprintf(stderr, "GPUs = %d does not divide Z = %d\n", ngpus, Z); exit(EXIT_FAILURE); }
+    for (r = 0; r < ngpus; r++) {
+        sn_params p = *base;
+        p.device = device + r; p.z0 = r * nz; p.nz = nz;
+        SN(sn_create(&p, &slab[r]));
+        slab_planes(lat, slabbuf, r * nz, nz);
+        SN(sn_set_lattice(slab[r], 0, slabbuf));
+        slab_planes(lat, ghost, r * nz - g, g);
+        SN(sn_set_ghost(slab[r], 0, 0, ghost));
+        slab_planes(lat, ghost, (r + 1) * nz, g);
+        SN(sn_set_ghost(slab[r], 0, 1, ghost));
+    }
+    for (r = 0; r < ngpus; r++) {
+        SN(sn_attach_peer(slab[r], 0, slab[(r + ngpus - 1) % ngpus]));
+        SN(sn_attach_peer(slab[r], 1, slab[(r + 1) % ngpus]));
+    }
+    free(ghost);
+    fprintf(stderr, "Z-slab decomposition: %d GPUs x %d planes, devices %d..%d\n", ngpus, nz, device, device + ngpus - 1);
+}
+
+static void engine_sweeps(sn_handle *h, long long n)                       /* MC_moves(MCMinorSteps), main.c:222,248 */
+{
+    int r;
+    if (ngpus == 1) { SN(sn_mc_sweeps(h, n)); return; }
+    for (r = 0; r < ngpus; r++) SN(sn_mc_sweeps(slab[r], n));             /* asynchronous: the slabs run concurrently */
+    analysis_stale = 1;
+}
+
+static void engine_sync(sn_handle *h)
+{
+    int r;
+    if (ngpus == 1) { SN(sn_synchronize(h)); return; }
+    for (r = 0; r < ngpus; r++) SN(sn_synchronize(slab[r]));
+}
+
+static void engine_set_efield(sn_handle *h, const float E[3])
+{
+    int r;
+    SN(sn_set_efield(h, 0, E));
+    for (r = 0; r < (ngpus > 1 ? ngpus : 0); r++) SN(sn_set_efield(slab[r], 0, E));
+}
+
+static void engine_polarisation(sn_handle *h, double P[3])
+{
+    int r, k; double Q[3];
+    if (ngpus == 1) { SN(sn_polarisation(h, 0, P)); return; }
+    P[0] = P[1] = P[2] = 0.0;
+    for (r = 0; r < ngpus; r++) { SN(sn_polarisation(slab[r], 0, Q)); for (k = 0; k < 3; k++) P[k] += Q[k] / ngpus; }
+}
+
+static void engine_counters(sn_handle *h, unsigned long long *acc, unsigned long long *rej, unsigned long long *vac)
+{
+    int r; unsigned long long a, b, c;
+    if (ngpus == 1) { SN(sn_get_counters(h, 0, acc, rej, vac)); return; }
+    *acc = *rej = *vac = 0;
+    for (r = 0; r < ngpus; r++) { SN(sn_get_counters(slab[r], 0, &a, &b, &c)); *acc += a; *rej += b; *vac += c; }
+}
+
+/* bring the full-lattice analysis handle up to date with the slabs (no-op on one GPU) */
+static void engine_gather(sn_handle *h)
+{
+    int r, x, y; const int nz = Z / ngpus;
+    if (ngpus == 1 || !analysis_stale) return;
+    for (r = 0; r < ngpus; r++) {
+        SN(sn_get_lattice(slab[r], 0, slabbuf));
+        for (x = 0; x < X; x++) for (y = 0; y < Y; y++)
+            memcpy(latbuf + site(x, y, r * nz) * 4, slabbuf + ((size_t)x * Y + y) * nz * 4, (size_t)nz * 4 * sizeof(float));
+    }
+    SN(sn_set_lattice(h, 0, latbuf));
+    analysis_stale = 0;
+}
+
 static void refresh_potential(sn_handle *h) { SN(sn_potential_map(h, 0, Vbuf)); }
 
 static void do_rdf(sn_handle *h, const char *fn)
@@ -291,6 +387,7 @@ static void analysis_midpoint(sn_handle *h, int MCstep, FILE *log)         /* ma
     char name[160], prefix[100];
     int need_v = CalculatePotential || SavePotentialCube || DisplayDumbTerminal;
     sprintf(prefix, "T_%04d_%d_%03d", T, (int)CageStrain, MCstep);       /* main.c:58 */
+    engine_gather(h);
     if (need_v) refresh_potential(h);
     if (DisplayDumbTerminal) terminal_summary();
     if (CalculateRecombination) do_recombination(h, log);                                   /* main.c:73 */
@@ -377,6 +474,7 @@ int main(int argc, char *argv[])
         p.beta = 1 / ((float)T / 300.0);                                   /* main.c:215 */
         p.ConstrainToX = ConstrainToX; p.DIM = DIM; p.nreplicas = 1; p.seed = SEED; p.device = device; p.kernel = kernel;
     }
+    if (ngpus > 1) { slabs_create(&p, latbuf); p.kernel = SN_KERNEL_COLOUR; }   /* the full-lattice handle only analyses */
     SN(sn_create(&p, &h));                                                 /* lattice malloc + gen_neighbour, main.c:155-180 */
     { int nnb = 0; SN(sn_neighbour_table(h, &nnb, NULL, NULL));
       fprintf(stderr, "\nNeighbour list generated: %d neighbours found with DipoleCutOff=%d.\n", nnb, DipoleCutOff); }
@@ -388,8 +486,9 @@ int main(int argc, char *argv[])
     fprintf(stderr, "\n\tMC startup. 'Do I dare disturb the universe?'\n");
     fprintf(stderr, "'.' is %e MC moves attempted.\n", (double)sweeps_per_megastep * (double)nsites);
     fprintf(stderr, "Equilibriation MC moves... %e\n", (double)sweeps_per_megastep * (double)nsites * (double)MCEqmSteps);
-    for (i = 0; i < MCEqmSteps; i++) { fprintf(stderr, ","); SN(sn_mc_sweeps(h, sweeps_per_megastep)); }   /* main.c:219-223 */
-    SN(sn_synchronize(h));
+    for (i = 0; i < MCEqmSteps; i++) { fprintf(stderr, ","); engine_sweeps(h, sweeps_per_megastep); }   /* main.c:219-223 */
+    engine_sync(h);
+    if (CalculateEfield || CalculatePotential || SaveDipolesSVG) engine_gather(h);
     if (CalculateEfield) write_efield_xyz(h, "equilib_lattice_efield.xyz", 4, 0);           /* main.c:225 */
     if (CalculatePotential) { refresh_potential(h); write_potential_png("equilib_pot.png", Vbuf); }
     if (SaveDipolesSVG) { SN(sn_get_lattice(h, 0, latbuf)); write_lattice_svg("equilib-SVG.svg", latbuf); }
@@ -401,19 +500,19 @@ int main(int argc, char *argv[])
             const double ph = (double)s / hyst_steps;                      /* 0..4 */
             const double e = hyst_amplitude * (ph < 1 ? ph : ph < 3 ? 2 - ph : ph - 4);
             float E[3] = {(float)e, (float)Efield[1], (float)Efield[2]}; double P[3];
-            SN(sn_set_efield(h, 0, E));
-            SN(sn_mc_sweeps(h, sweeps_per_megastep));
-            SN(sn_polarisation(h, 0, P));
+            engine_set_efield(h, E);
+            engine_sweeps(h, sweeps_per_megastep);
+            engine_polarisation(h, P);
             fprintf(stdout, "T: %d Efield: x %f Polar: %f\n", T, e, P[0]);
         }
-        { float E[3] = {(float)Efield[0], (float)Efield[1], (float)Efield[2]}; SN(sn_set_efield(h, 0, E)); }
+        { float E[3] = {(float)Efield[0], (float)Efield[1], (float)Efield[2]}; engine_set_efield(h, E); }
         fflush(stdout);
     }
 
     for (i = 0; i < MCMegaSteps; i++) {                                    /* main.c:244-265, the hot loop */
         double tic = now_s(), toc, tac;
-        SN(sn_mc_sweeps(h, sweeps_per_megastep));
-        SN(sn_synchronize(h));
+        engine_sweeps(h, sweeps_per_megastep);
+        engine_sync(h);
         toc = now_s();
         analysis_midpoint(h, i, log);
         fflush(stdout);
@@ -422,11 +521,12 @@ int main(int argc, char *argv[])
         fprintf(stderr, "Output routines: %f s ; Efficiency of MC moves vs. analysis %.2f%%\n", tac - toc, 100.0 * (toc - tic) / (tac - tic));
     }
     fprintf(stderr, "\n");
-    SN(sn_get_counters(h, 0, &acc, &rej, &vac));
+    engine_counters(h, &acc, &rej, &vac);
     fprintf(stderr, "Monte Carlo moves - ACCEPT: %llu REJECT: %llu ratio: %f\n", acc, rej, (float)acc / (float)(rej + acc));
     fprintf(stderr, " For us, there is only the trying. The rest is not our business. ~T.S.Eliot\n\n");
     if (log) fclose(log);
     SN(sn_destroy(h));
-    free(latbuf); free(Vbuf);
+    for (i = 0; i < (ngpus > 1 ? ngpus : 0); i++) SN(sn_destroy(slab[i]));
+    free(latbuf); free(Vbuf); free(slabbuf);
     return 0;
 }

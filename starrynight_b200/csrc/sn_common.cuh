@@ -19,6 +19,7 @@
 #include "../../include/starrynight_b200.h"
 
 #define SN_FLAGS_NEXT 32        // h->flags[32..33]: the tiled kernel's work counter (u64)
+#define SN_FLAGS_SPECIES 40     // h->flags[40]: result of the species scan in sn_set_lattice
 #define SN_FLAGS_VER 64         // h->flags[64..]: tile versions, [rep][X/16][Y/16][nz/16 + 2]
 #define SN_MAX_NB 1024          // neighbour-table capacity in constant memory (cutoff <= 6)
 

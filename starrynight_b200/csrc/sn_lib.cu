@@ -213,6 +213,17 @@ int sn_refresh_ghosts(sn_handle *h)
 }
 
 // strided copy between the host's dense [X][Y][nz] float4 block and the padded device array
+__global__ void __launch_bounds__(256) sn_species_scan_kernel(const float4 *__restrict__ lat, const SnGeom G, unsigned int *__restrict__ flag)
+{
+    const long long n = (long long)G.X * G.Y * G.nz;
+    bool nonunit = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % G.nz), y = (int)((i / G.nz) % G.Y), x = (int)(i / ((long long)G.nz * G.Y));
+        nonunit |= lat[sn_pidx(G, x, y, z)].w != 1.0f;
+    }
+    if (__any_sync(0xffffffffu, nonunit) && (threadIdx.x & 31) == 0) *flag = 1u;
+}
+
 static int sn_copy_block(sn_handle *h, int replica, float *host, bool to_device)
 {
     const SnGeom &G = h->G;
@@ -237,12 +248,16 @@ extern "C" int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen)
     h->lat2_valid = false;
     if ((rc = sn_copy_block(h, replica, const_cast<float *>(xyzlen), true))) return rc;
     if ((rc = sn_refresh_ghosts(h))) return rc;
-    // does any replica carry species (length != 1)?  decides the kernel specialisation
+    // does any replica carry species (length != 1)?  decides the kernel specialisation (scanned on the device:
+    // a host loop over 512^3 sites costs more than the upload itself)
     {
-        const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
-        bool nonunit = false;
-        for (long long i = 0; i < n; i++) if (xyzlen[4 * i + 3] != 1.0f) { nonunit = true; break; }
-        h->rep_species[replica] = nonunit;
+        unsigned int nonunit = 0, *d_flag = h->flags + SN_FLAGS_SPECIES;
+        SN_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned int), h->stream));
+        sn_species_scan_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_flag);
+        SN_CUDA_CHECK(cudaGetLastError());
+        SN_CUDA_CHECK(cudaMemcpyAsync(&nonunit, d_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+        SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        h->rep_species[replica] = nonunit != 0;
         h->species = false;
         for (int r = 0; r < h->p.nreplicas; r++) h->species = h->species || h->rep_species[r];
     }

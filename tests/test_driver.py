@@ -109,7 +109,8 @@ def test_driver_efield_maps_and_recombination_log(built, tmp_path):
         cfg += "\nCalculateEfield: true\n"
     if "CalculateRecombination: true" not in cfg:
         cfg += "\nCalculateRecombination: true\n"
-    cfg = cfg.replace("MCMegaSteps: 20", "MCMegaSteps: 2").replace("MCEqmSteps: 5", "MCEqmSteps: 1").replace("MCMoves: 200.0", "MCMoves: 2.0")
+    cfg = cfg.replace("MCMegaSteps: 1", "MCMegaSteps: 2")                  # the stored cfg is the shortened one (1 / 1 / 2.0)
+    assert "MCMegaSteps: 2" in cfg and "CalculateEfield: true" in cfg and "X=12" in cfg
     (tmp_path / "starrynight.cfg").write_text(cfg)
     run = subprocess.run([DRIVER], cwd=tmp_path, capture_output=True, text=True)
     assert run.returncode == 0, run.stderr[-2000:]
@@ -128,3 +129,34 @@ def test_driver_efield_maps_and_recombination_log(built, tmp_path):
     log = (tmp_path / "Recombination_T_0300.log").read_text().splitlines()
     rows = [l for l in log if l.startswith("T: 300 ZBe:")]
     assert len(rows) == 2 and all("R_FD:" in l and "FD-Total-hole:" in l for l in rows)
+
+
+@pytest.mark.gpu
+def test_driver_two_gpu_slabs_write_identical_files(built, tmp_path):
+    """GPUs = 2 (Z-slabs, boundary pushes over NVLink) must reproduce the single-GPU run file for file:
+    the decomposed chain is bit-identical and the analysis runs on the gathered lattice."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = ref_files()["starrynight.cfg"].decode()
+    cfg = cfg.replace("X=20", "X=32").replace("Y=20", "Y=32").replace("Z=28", "Z=64").replace('"antiferro_wall"', '"random"')
+    cfg = cfg.replace("MCMegaSteps: 1", "MCMegaSteps: 2").replace("MCMoves: 2.0", "MCMoves: 3.0")
+    assert "MCMegaSteps: 2" in cfg and "MCMoves: 3.0" in cfg and "Z=64" in cfg
+    cfg += '\nHysteresis : { amplitude = 0.1; steps = 2; cycles = 1; };\n'
+    outs = []
+    for n in (1, 2):
+        d = tmp_path / f"gpus{n}"
+        d.mkdir()
+        (d / "starrynight.cfg").write_text(cfg + f"\nGPUs = {n};\n")
+        run = subprocess.run([DRIVER], cwd=d, capture_output=True, text=True)
+        assert run.returncode == 0, run.stderr[-2000:]
+        if n == 2:
+            assert "Z-slab decomposition: 2 GPUs x 32 planes" in run.stderr
+        files = {fn: (d / fn).read_bytes() for fn in sorted(os.listdir(d)) if not fn.startswith("Recombination") and fn != "starrynight.cfg"}
+        acc = [l for l in run.stderr.splitlines() if "ACCEPT:" in l][0]
+        outs.append((files, run.stdout, acc))
+    assert outs[0][0].keys() == outs[1][0].keys() and len(outs[0][0]) >= 8
+    for fn in outs[0][0]:
+        assert outs[0][0][fn] == outs[1][0][fn], fn
+    assert outs[0][1] == outs[1][1] and "Polar:" in outs[0][1]          # hysteresis trace (main.c:82 format)
+    assert outs[0][2] == outs[1][2]
