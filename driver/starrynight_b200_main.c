@@ -19,6 +19,10 @@
  *   Seed (int)          Philox / MT seed instead of 0xDEADBEEF + T
  *   Device (int)        CUDA device ordinal
  *   Kernel (string)     "auto" | "colour" | "tiled"
+ *   Checkpoint (string) file rewritten after every production mega-step: lattice, sweeps done (the Philox
+ *                       counter), ACCEPT / REJECT and the index of the next mega-step
+ *   Restart (string)    continue from such a file: skips the initial analysis, equilibration and hysteresis
+ *                       and resumes the production loop where the checkpoint left it, bit for bit
  *   GPUs (int)          Z-slab decomposition over this many GPUs of the box (devices Device, Device+1, ...):
  *                       one slab handle per GPU, boundary updates pushed GPU-to-GPU over NVLink by the sweep
  *                       kernels; the chain is bit-identical to the single-GPU one.  Z must be a multiple of
@@ -55,6 +59,7 @@ static float dip_length[10], dip_prevalence[10];
 static int dipolecount = 0;
 static long long seed_override = -1;
 static int device = 0, kernel = SN_KERNEL_AUTO, ngpus = 1;
+static const char *checkpoint_path = NULL, *restart_path = NULL;
 static double hyst_amplitude = 0.0;
 static int hyst_steps = 0, hyst_cycles = 1;
 
@@ -117,6 +122,8 @@ static void load_config(const char *path)
     if (ngpus < 1 || ngpus > 16) { fprintf(stderr, "GPUs = %d outside 1..16\n", ngpus); exit(EXIT_FAILURE); }
     if (snc_lookup_string(&cfg, "Kernel", &str))
         kernel = !strcmp(str, "colour") ? SN_KERNEL_COLOUR : !strcmp(str, "tiled") ? SN_KERNEL_TILED : SN_KERNEL_AUTO;
+    if (snc_lookup_string(&cfg, "Checkpoint", &str)) checkpoint_path = strdup(str);
+    if (snc_lookup_string(&cfg, "Restart", &str)) restart_path = strdup(str);
     snc_lookup_float(&cfg, "Hysteresis.amplitude", &hyst_amplitude);
     snc_lookup_int(&cfg, "Hysteresis.steps", &hyst_steps);
     snc_lookup_int(&cfg, "Hysteresis.cycles", &hyst_cycles);
@@ -409,6 +416,46 @@ static void analysis_midpoint(sn_handle *h, int MCstep, FILE *log)         /* ma
     if (SaveDipolesSVG) write_lattice_svg(name, latbuf);
 }
 
+/* ---- checkpoint / restart ------------------------------------------------------------- */
+typedef struct {
+    char magic[8];                       /* "SNB200C1" */
+    int X, Y, Z, T;
+    unsigned long long seed, sweeps, accept, reject, vacant;
+    int next_megastep, pad;
+} sn_checkpoint_header;
+
+static void engine_counters(sn_handle *h, unsigned long long *acc, unsigned long long *rej, unsigned long long *vac);
+
+static void checkpoint_write(sn_handle *h, unsigned long long seed, int next_megastep)
+{
+    sn_checkpoint_header hd; char tmp[512]; FILE *f; const size_t n = (size_t)X * Y * Z * 4;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, "SNB200C1", 8);
+    hd.X = X; hd.Y = Y; hd.Z = Z; hd.T = T; hd.seed = seed; hd.next_megastep = next_megastep;
+    if (ngpus > 1) { analysis_stale = 1; engine_gather(h); SN(sn_get_sweep_count(slab[0], &hd.sweeps)); }   /* gather fills latbuf */
+    else { SN(sn_get_lattice(h, 0, latbuf)); SN(sn_get_sweep_count(h, &hd.sweeps)); }
+    engine_counters(h, &hd.accept, &hd.reject, &hd.vacant);
+    snprintf(tmp, sizeof tmp, "%s.tmp", checkpoint_path);
+    f = fopen(tmp, "wb");
+    if (!f || fwrite(&hd, sizeof hd, 1, f) != 1 || fwrite(latbuf, sizeof(float), n, f) != n) { perror(tmp); exit(EXIT_FAILURE); }
+    fclose(f);
+    if (rename(tmp, checkpoint_path)) { perror(checkpoint_path); exit(EXIT_FAILURE); }   /* never a half-written checkpoint */
+}
+
+static void checkpoint_read(sn_checkpoint_header *hd, unsigned long long seed)
+{
+    FILE *f = fopen(restart_path, "rb"); const size_t n = (size_t)X * Y * Z * 4;
+    if (!f || fread(hd, sizeof *hd, 1, f) != 1 || memcmp(hd->magic, "SNB200C1", 8)) { fprintf(stderr, "Restart: cannot read '%s'\n", restart_path); exit(EXIT_FAILURE); }
+    if (hd->X != X || hd->Y != Y || hd->Z != Z || hd->T != T || hd->seed != seed) {
+        fprintf(stderr, "Restart: '%s' holds a %dx%dx%d lattice at T=%d, seed %llX; the configuration asks for %dx%dx%d, T=%d, seed %llX\n",
+                restart_path, hd->X, hd->Y, hd->Z, hd->T, hd->seed, X, Y, Z, T, seed);
+        exit(EXIT_FAILURE);
+    }
+    if (fread(latbuf, sizeof(float), n, f) != n) { fprintf(stderr, "Restart: '%s' is truncated\n", restart_path); exit(EXIT_FAILURE); }
+    fclose(f);
+    fprintf(stderr, "Restart from '%s': %llu sweeps done, next mega-step %d\n", restart_path, hd->sweeps, hd->next_megastep);
+}
+
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 int main(int argc, char *argv[])
@@ -423,7 +470,9 @@ int main(int argc, char *argv[])
     long long sweeps_per_megastep;
     unsigned long long acc = 0, rej = 0, vac = 0;
     size_t nsites;
-    int histo[10];
+    int histo[10], first_megastep = 0;
+    unsigned long long run_seed = 0;
+    sn_checkpoint_header ck;
 
     fprintf(stderr, "Starry Night - Monte Carlo brushstrokes (B200 build: %s).\n", sn_version());
     for (i = 1; i < argc; i++)
@@ -457,6 +506,8 @@ int main(int argc, char *argv[])
         fprintf(stderr, "\nSolid Solution: ");
         for (i = 0; i < dipolecount; i++) fprintf(stderr, "    Dipole %d: Length: %f Count: %d", i, dip_length[i], histo[i]);
         fprintf(stderr, "\nSolid solution formed...\n");
+        run_seed = SEED;
+        if (restart_path && !init_only) checkpoint_read(&ck, SEED);       /* replaces the freshly built lattice */
         if (init_only) {
             FILE *f = fopen(init_only, "wb");
             if (!f || fwrite(latbuf, sizeof(float), nsites * 4, f) != nsites * 4) { perror(init_only); return EXIT_FAILURE; }
@@ -479,13 +530,20 @@ int main(int argc, char *argv[])
     { int nnb = 0; SN(sn_neighbour_table(h, &nnb, NULL, NULL));
       fprintf(stderr, "\nNeighbour list generated: %d neighbours found with DipoleCutOff=%d.\n", nnb, DipoleCutOff); }
     SN(sn_set_lattice(h, 0, latbuf));
-    analysis_initial(h);
+    if (restart_path) {
+        int r;
+        SN(sn_set_sweep_count(h, ck.sweeps));
+        SN(sn_set_counters(ngpus > 1 ? slab[0] : h, 0, ck.accept, ck.reject, ck.vacant));
+        for (r = 0; r < (ngpus > 1 ? ngpus : 0); r++) SN(sn_set_sweep_count(slab[r], ck.sweeps));
+        first_megastep = ck.next_megastep;
+    } else analysis_initial(h);
 
     sweeps_per_megastep = (long long)(MCMegaMultiplier + 0.5);             /* MCMinorSteps = X*Y*Z*MCMoves attempts, config.c:166 */
     if (sweeps_per_megastep < 1 && MCMegaMultiplier > 0) sweeps_per_megastep = 1;
     fprintf(stderr, "\n\tMC startup. 'Do I dare disturb the universe?'\n");
     fprintf(stderr, "'.' is %e MC moves attempted.\n", (double)sweeps_per_megastep * (double)nsites);
     fprintf(stderr, "Equilibriation MC moves... %e\n", (double)sweeps_per_megastep * (double)nsites * (double)MCEqmSteps);
+    if (restart_path) goto production;
     for (i = 0; i < MCEqmSteps; i++) { fprintf(stderr, ","); engine_sweeps(h, sweeps_per_megastep); }   /* main.c:219-223 */
     engine_sync(h);
     if (CalculateEfield || CalculatePotential || SaveDipolesSVG) engine_gather(h);
@@ -509,7 +567,8 @@ int main(int argc, char *argv[])
         fflush(stdout);
     }
 
-    for (i = 0; i < MCMegaSteps; i++) {                                    /* main.c:244-265, the hot loop */
+production:
+    for (i = first_megastep; i < MCMegaSteps; i++) {                       /* main.c:244-265, the hot loop */
         double tic = now_s(), toc, tac;
         engine_sweeps(h, sweeps_per_megastep);
         engine_sync(h);
@@ -519,6 +578,7 @@ int main(int argc, char *argv[])
         tac = now_s();
         fprintf(stderr, "MC Moves (per second): %f MHz\n", 1e-6 * (double)sweeps_per_megastep * (double)nsites / (toc - tic));
         fprintf(stderr, "Output routines: %f s ; Efficiency of MC moves vs. analysis %.2f%%\n", tac - toc, 100.0 * (toc - tic) / (tac - tic));
+        if (checkpoint_path) checkpoint_write(h, run_seed, i + 1);
     }
     fprintf(stderr, "\n");
     engine_counters(h, &acc, &rej, &vac);

@@ -128,6 +128,16 @@ SN_API int sn_synchronize(sn_handle *h);
 SN_API int sn_get_counters(sn_handle *h, int replica, unsigned long long *accept,
                     unsigned long long *reject, unsigned long long *vacant);
 SN_API int sn_reset_counters(sn_handle *h);
+SN_API int sn_set_counters(sn_handle *h, int replica, unsigned long long accept, unsigned long long reject,
+                    unsigned long long vacant);
+
+/* Checkpoint / restart (the reference has none; long runs on large lattices need it).  The state of the
+ * chain is the lattice (sn_get_lattice / sn_set_lattice), the counters above and the number of sweeps done,
+ * which is the counter word of the per-site Philox streams: a handle created with the same parameters and
+ * seed, given the saved lattice and sweep count, continues the chain bit for bit.  On Z-slab handles call
+ * sn_set_sweep_count on every slab before the next sn_mc_sweeps. */
+SN_API int sn_get_sweep_count(sn_handle *h, unsigned long long *sweeps_done);
+SN_API int sn_set_sweep_count(sn_handle *h, unsigned long long sweeps_done);
 
 /* audit of site_energy (montecarlo-core.c:76-141): dE[i] of rotating site
  * sites[3i..3i+2] = (x, y, zlocal) to newdip[3i..3i+2], lattice unchanged. */

@@ -146,6 +146,7 @@ struct sn_handle {
     float4 *peer_lat[2] = {nullptr, nullptr};       // lower / upper neighbour's padded lattice
     unsigned int *flags = nullptr;                  // own phase flags [0,1], work counter, tile versions (device; SN_FLAGS_*)
     unsigned int *peer_flags[2] = {nullptr, nullptr};
+    size_t nver = 0;                                // entries of the tile-version array behind SN_FLAGS_VER
     unsigned int phase_epoch = 0;
     bool peer_is_ipc[2] = {false, false};
     unsigned char ipc_key[2][64] = {};

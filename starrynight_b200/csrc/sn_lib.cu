@@ -139,7 +139,8 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
         // slab neighbour reaches all of it through one IPC handle)
         size_t nflags = SN_FLAGS_VER;
         if (G.X % 32 == 0 && G.Y % 32 == 0 && G.nz % 32 == 0)
-            nflags += (size_t)p->nreplicas * (G.X / 16) * (G.Y / 16) * (G.nz / 16 + 2);
+            h->nver = (size_t)p->nreplicas * (G.X / 16) * (G.Y / 16) * (G.nz / 16 + 2);
+        nflags += h->nver;
         SN_CUDA_CHECK(cudaMalloc(&h->flags, sizeof(unsigned int) * nflags));
         SN_CUDA_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(unsigned int) * nflags, h->stream));
     }
@@ -407,6 +408,44 @@ extern "C" int sn_reset_counters(sn_handle *h)
 {
     SN_CHECK_HANDLE(h, 0);
     SN_CUDA_CHECK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long) * 3 * h->p.nreplicas, h->stream));
+    return SN_OK;
+}
+
+// ---- checkpoint / restart -----------------------------------------------------------
+// The chain's state is the lattice (sn_get_lattice), the number of sweeps done -- the Philox counter word,
+// and the version of every tile in the dataflow kernel -- and the ACCEPT / REJECT counters.
+__global__ void sn_fill_u32_kernel(unsigned int *p, long long n, unsigned int v)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+extern "C" int sn_get_sweep_count(sn_handle *h, unsigned long long *sweeps)
+{
+    SN_CHECK_HANDLE(h, 0);
+    if (!sweeps) return sn_fail(SN_ERR_INVALID, "sn_get_sweep_count: null");
+    *sweeps = h->sweep;
+    return SN_OK;
+}
+
+extern "C" int sn_set_sweep_count(sn_handle *h, unsigned long long sweeps)
+{
+    SN_CHECK_HANDLE(h, 0);
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->sweep = sweeps;
+    if (h->nver > 0) {                               // every tile (ghost layers included) has completed `sweeps` sweeps
+        sn_fill_u32_kernel<<<64, 256, 0, h->stream>>>(h->flags + SN_FLAGS_VER, (long long)h->nver, (unsigned int)sweeps);
+        SN_CUDA_CHECK(cudaGetLastError());
+        SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    return SN_OK;
+}
+
+extern "C" int sn_set_counters(sn_handle *h, int replica, unsigned long long accept, unsigned long long reject, unsigned long long vacant)
+{
+    SN_CHECK_HANDLE(h, replica);
+    const unsigned long long c[3] = {accept, reject, vacant};
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->counters + 3 * replica, c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return SN_OK;
 }
 

@@ -160,3 +160,29 @@ def test_driver_two_gpu_slabs_write_identical_files(built, tmp_path):
         assert outs[0][0][fn] == outs[1][0][fn], fn
     assert outs[0][1] == outs[1][1] and "Polar:" in outs[0][1]          # hysteresis trace (main.c:82 format)
     assert outs[0][2] == outs[1][2]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(20, 20, 28), (32, 32, 32)])
+def test_driver_checkpoint_restart_continues_the_chain(built, tmp_path, shape):
+    """Checkpoint after every mega-step, Restart from it: the resumed run writes the same later files as an
+    uninterrupted one (lattice + sweep counter = Philox counter + ACCEPT/REJECT is the whole state).  Both
+    sweep kernels: 20x20x28 runs colour passes, 32^3 the tiled dataflow kernel (tile versions restored)."""
+    X, Y, Z = shape
+    cfg = ref_files()["starrynight.cfg"].decode()
+    cfg = cfg.replace("X=20", f"X={X}").replace("Y=20", f"Y={Y}").replace("Z=28", f"Z={Z}").replace('"antiferro_wall"', '"random"')
+    runs = {}
+    for name, steps, extra in (("full", 4, ""), ("first", 2, 'Checkpoint = "ck.bin";'), ("resumed", 4, 'Restart = "../first/ck.bin";')):
+        d = tmp_path / name
+        d.mkdir()
+        (d / "starrynight.cfg").write_text(cfg.replace("MCMegaSteps: 1", f"MCMegaSteps: {steps}") + "\n" + extra + "\n")
+        run = subprocess.run([DRIVER], cwd=d, capture_output=True, text=True)
+        assert run.returncode == 0, run.stderr[-2000:]
+        runs[name] = (d, [l for l in run.stderr.splitlines() if "ACCEPT:" in l][0])
+        assert ("Restart from" in run.stderr) == (name == "resumed")
+    for step in (2, 3):
+        for suffix in ("_potential.xyz", "-RDF.dat", "_potential.png"):
+            fn = f"T_0300_1_{step:03d}{suffix}"
+            assert (runs["full"][0] / fn).read_bytes() == (runs["resumed"][0] / fn).read_bytes(), fn
+    assert not (runs["resumed"][0] / "T_0300_1_001_potential.xyz").exists()      # resumed at mega-step 2
+    assert runs["full"][1] == runs["resumed"][1]                                   # counters carried over
