@@ -245,5 +245,7 @@ static int snc_length(const snc_node *n)
 /* strict: a non-float element yields 0.0, like config_setting_get_float_elem */
 static double snc_get_float_elem(const snc_node *n, int i)
 { if (!n || i < 0 || i >= snc_length(n) || n->child[i]->type != SNC_FLOAT) return 0.0; return n->child[i]->fval; }
+static long long snc_get_int_elem(const snc_node *n, int i)
+{ if (!n || i < 0 || i >= snc_length(n) || n->child[i]->type != SNC_INT) return 0; return n->child[i]->ival; }
 
 #endif /* SN_CFG_H */

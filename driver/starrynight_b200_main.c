@@ -19,6 +19,10 @@
  *   Seed (int)          Philox / MT seed instead of 0xDEADBEEF + T
  *   Device (int)        CUDA device ordinal
  *   Kernel (string)     "auto" | "colour" | "tiled"
+ *   Temperatures (int array)   run all these temperatures at once as replicas of one handle (one batch of
+ *                       kernels instead of the reference's one process per T, Makefile:49-63).  Every replica
+ *                       is initialised and seeded (0xDEADBEEF + T) exactly like a separate run at that T and
+ *                       writes that run's T-tagged files, bit for bit.  Overrides T and argv[1].
  *   Checkpoint (string) file rewritten after every production mega-step: lattice, sweeps done (the Philox
  *                       counter), ACCEPT / REJECT and the index of the next mega-step
  *   Restart (string)    continue from such a file: skips the initial analysis, equilibration and hysteresis
@@ -60,6 +64,7 @@ static int dipolecount = 0;
 static long long seed_override = -1;
 static int device = 0, kernel = SN_KERNEL_AUTO, ngpus = 1;
 static const char *checkpoint_path = NULL, *restart_path = NULL;
+static int nT = 0, Ts[64];
 static double hyst_amplitude = 0.0;
 static int hyst_steps = 0, hyst_cycles = 1;
 
@@ -122,6 +127,10 @@ static void load_config(const char *path)
     if (ngpus < 1 || ngpus > 16) { fprintf(stderr, "GPUs = %d outside 1..16\n", ngpus); exit(EXIT_FAILURE); }
     if (snc_lookup_string(&cfg, "Kernel", &str))
         kernel = !strcmp(str, "colour") ? SN_KERNEL_COLOUR : !strcmp(str, "tiled") ? SN_KERNEL_TILED : SN_KERNEL_AUTO;
+    s = snc_lookup(&cfg, "Temperatures");
+    nT = s ? snc_length(s) : 0;
+    if (nT > 64) nT = 64;
+    for (i = 0; i < nT; i++) Ts[i] = (int)snc_get_int_elem(s, i);
     if (snc_lookup_string(&cfg, "Checkpoint", &str)) checkpoint_path = strdup(str);
     if (snc_lookup_string(&cfg, "Restart", &str)) restart_path = strdup(str);
     snc_lookup_float(&cfg, "Hysteresis.amplitude", &hyst_amplitude);
@@ -238,6 +247,7 @@ static void write_lattice_ppm_hsv(const char *fn, const float *lat)       /* ana
 /* ---- analysis hooks, main.c:29-122 ------------------------------------------------ */
 static double *Vbuf;
 static float *latbuf;
+static int cur = 0;                       /* replica the analysis routines look at (temperature batches) */
 
 /* ---- the sweep engine: one handle, or GPUs slab handles + a full-lattice analysis handle ---- */
 static sn_handle *slab[16];
@@ -294,14 +304,14 @@ static void engine_sync(sn_handle *h)
 static void engine_set_efield(sn_handle *h, const float E[3])
 {
     int r;
-    SN(sn_set_efield(h, 0, E));
+    for (r = 0; r < (nT > 1 ? nT : 1); r++) SN(sn_set_efield(h, r, E));
     for (r = 0; r < (ngpus > 1 ? ngpus : 0); r++) SN(sn_set_efield(slab[r], 0, E));
 }
 
 static void engine_polarisation(sn_handle *h, double P[3])
 {
     int r, k; double Q[3];
-    if (ngpus == 1) { SN(sn_polarisation(h, 0, P)); return; }
+    if (ngpus == 1) { SN(sn_polarisation(h, cur, P)); return; }
     P[0] = P[1] = P[2] = 0.0;
     for (r = 0; r < ngpus; r++) { SN(sn_polarisation(slab[r], 0, Q)); for (k = 0; k < 3; k++) P[k] += Q[k] / ngpus; }
 }
@@ -309,7 +319,7 @@ static void engine_polarisation(sn_handle *h, double P[3])
 static void engine_counters(sn_handle *h, unsigned long long *acc, unsigned long long *rej, unsigned long long *vac)
 {
     int r; unsigned long long a, b, c;
-    if (ngpus == 1) { SN(sn_get_counters(h, 0, acc, rej, vac)); return; }
+    if (ngpus == 1) { SN(sn_get_counters(h, cur, acc, rej, vac)); return; }
     *acc = *rej = *vac = 0;
     for (r = 0; r < ngpus; r++) { SN(sn_get_counters(slab[r], 0, &a, &b, &c)); *acc += a; *rej += b; *vac += c; }
 }
@@ -328,19 +338,19 @@ static void engine_gather(sn_handle *h)
     analysis_stale = 0;
 }
 
-static void refresh_potential(sn_handle *h) { SN(sn_potential_map(h, 0, Vbuf)); }
+static void refresh_potential(sn_handle *h) { SN(sn_potential_map(h, cur, Vbuf)); }
 
 static void do_rdf(sn_handle *h, const char *fn)
 {
     double fe[SN_RDF_BINS], afe[SN_RDF_BINS]; long long cnt[SN_RDF_BINS];
-    SN(sn_rdf(h, 0, fe, afe, cnt));
+    SN(sn_rdf(h, cur, fe, afe, cnt));
     write_rdf(fn, fe, afe, cnt);
 }
 
 static void write_efield_xyz(sn_handle *h, const char *fn, int cutoff, int half_offset)   /* analysis.c:379-389, 468-479 */
 {
     FILE *fo; int x, y, z;
-    SN(sn_efield_map(h, 0, cutoff, half_offset, Vbuf));
+    SN(sn_efield_map(h, cur, cutoff, half_offset, Vbuf));
     fo = fopen(fn, "w");
     if (!fo) { perror(fn); return; }
     for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++) fprintf(fo, "%d %d %d %f\n", x, y, z, Vbuf[site(x, y, z)]);
@@ -350,7 +360,7 @@ static void write_efield_xyz(sn_handle *h, const char *fn, int cutoff, int half_
 static void do_recombination(sn_handle *h, FILE *log)                      /* analysis.c:96-228 */
 {
     double r[SN_RECOMB_N];
-    SN(sn_recombination(h, 0, r));
+    SN(sn_recombination(h, cur, r));
     if (log) {
         fprintf(log, "T: %d ZBe: %e ZBh: %e ZFDe: %e ZFDh: %e R_Boltz: %e ", T, r[0], r[1], r[2], r[3], r[4]);
         fprintf(log, "R_FD: %e FD-Total-electron: %e FD-Total-hole: %e\n", r[5], r[6], r[7]);
@@ -379,7 +389,7 @@ static void analysis_initial(sn_handle *h)                                 /* ma
     if (need_v) refresh_potential(h);
     if (CalculatePotential) write_potential_xyz("initial_lattice_potential.xyz", Vbuf);
     if (SavePotentialCube) write_potential_cube("initial_lattice_potential.cube", Vbuf);
-    if (SaveDipolesSVG || SaveDipolesPNG || SaveDipolesXYZ) SN(sn_get_lattice(h, 0, latbuf));
+    if (SaveDipolesSVG || SaveDipolesPNG || SaveDipolesXYZ) SN(sn_get_lattice(h, cur, latbuf));
     if (SaveDipolesSVG) write_lattice_svg("initial-SVG.svg", latbuf);
     if (CalculatePotential) write_potential_png("initial_pot.png", Vbuf);
     if (SaveDipolesXYZ) write_lattice_xyz("initial_dipoles.xyz", latbuf);
@@ -409,7 +419,7 @@ static void analysis_midpoint(sn_handle *h, int MCstep, FILE *log)         /* ma
     if (SavePotentialCube) write_potential_cube(name, Vbuf);
     sprintf(name, "%s_potential.png", prefix);
     if (CalculatePotential) write_potential_png(name, Vbuf);
-    if (SaveDipolesPNG || SaveDipolesSVG) SN(sn_get_lattice(h, 0, latbuf));
+    if (SaveDipolesPNG || SaveDipolesSVG) SN(sn_get_lattice(h, cur, latbuf));
     sprintf(name, "%s_MC-PNG.png", prefix);
     if (SaveDipolesPNG) write_lattice_ppm_hsv(name, latbuf);
     sprintf(name, "%s_MC-SVG.svg", prefix);
@@ -463,7 +473,8 @@ int main(int argc, char *argv[])
     const char *init_only = NULL, *cfgpath = "starrynight.cfg";
     int i, npos = 0;
     char name[160];
-    FILE *log;
+    FILE *log, *logs[64];
+    int r;
     sn_mt19937 mt;
     sn_params p;
     sn_handle *h = NULL;
@@ -486,6 +497,11 @@ int main(int argc, char *argv[])
         if (npos == 0) { sscanf(argv[i], "%d", &T); fprintf(stderr, "Command line temperature: T = %d\n", T); }
         if (npos == 1) { sscanf(argv[i], "%lf", &CageStrain); fprintf(stderr, "Command Line CageStrain: CageStrain = %lf\n", CageStrain); }
         npos++;
+    }
+    if (nT > 0) T = Ts[0]; else { nT = 1; Ts[0] = T; }
+    if (nT > 1 && (ngpus > 1 || checkpoint_path || restart_path || seed_override >= 0)) {
+        fprintf(stderr, "Temperatures cannot be combined with GPUs > 1, Checkpoint, Restart or Seed\n");
+        return EXIT_FAILURE;
     }
     nsites = (size_t)X * Y * Z;
     fprintf(stderr, "Memory allocation for lattice with X=%d Y=%d Z=%d\n", X, Y, Z);
@@ -523,20 +539,35 @@ int main(int argc, char *argv[])
         p.X = X; p.Y = Y; p.Z = Z; p.cutoff = DipoleCutOff; p.CageStrain = CageStrain; p.K = K;
         p.Efield[0] = (float)Efield[0]; p.Efield[1] = (float)Efield[1]; p.Efield[2] = (float)Efield[2];
         p.beta = 1 / ((float)T / 300.0);                                   /* main.c:215 */
-        p.ConstrainToX = ConstrainToX; p.DIM = DIM; p.nreplicas = 1; p.seed = SEED; p.device = device; p.kernel = kernel;
+        p.ConstrainToX = ConstrainToX; p.DIM = DIM; p.nreplicas = nT; p.seed = SEED; p.device = device; p.kernel = kernel;
+        logs[0] = log;
     }
     if (ngpus > 1) { slabs_create(&p, latbuf); p.kernel = SN_KERNEL_COLOUR; }   /* the full-lattice handle only analyses */
     SN(sn_create(&p, &h));                                                 /* lattice malloc + gen_neighbour, main.c:155-180 */
     { int nnb = 0; SN(sn_neighbour_table(h, &nnb, NULL, NULL));
       fprintf(stderr, "\nNeighbour list generated: %d neighbours found with DipoleCutOff=%d.\n", nnb, DipoleCutOff); }
     SN(sn_set_lattice(h, 0, latbuf));
+    for (r = 1; r < nT; r++) {
+        /* the other temperatures of the batch: initial state, seed and log of a separate run at Ts[r] (main.c:165-215) */
+        const unsigned int SEED = (unsigned int)(0xDEADBEEFu + (unsigned int)Ts[r]);
+        sn_mt_seed(&mt, SEED);
+        if (!sn_init_lattice(latbuf, X, Y, Z, DIM, InitialLattice, &mt)) sn_init_lattice(latbuf, X, Y, Z, DIM, "random", &mt);
+        sn_init_solid_solution(latbuf, X, Y, Z, dipolecount, dip_length, dip_prevalence, &mt, histo);
+        SN(sn_set_lattice(h, r, latbuf));
+        SN(sn_set_beta(h, r, 1 / ((float)Ts[r] / 300.0)));
+        SN(sn_set_replica_seed(h, r, SEED));
+        sprintf(name, "Recombination_T_%04d.log", Ts[r]);
+        logs[r] = fopen(name, "w");
+        if (logs[r]) fprintf(logs[r], "# Starrynight - simulation run on time(NULL)= %ld\n# Mersenne Twister Seed: %X\n", (long)time(NULL), SEED);
+    }
+    if (nT > 1) fprintf(stderr, "Temperature batch: %d replicas, T = %d .. %d\n", nT, Ts[0], Ts[nT - 1]);
     if (restart_path) {
-        int r;
         SN(sn_set_sweep_count(h, ck.sweeps));
         SN(sn_set_counters(ngpus > 1 ? slab[0] : h, 0, ck.accept, ck.reject, ck.vacant));
         for (r = 0; r < (ngpus > 1 ? ngpus : 0); r++) SN(sn_set_sweep_count(slab[r], ck.sweeps));
         first_megastep = ck.next_megastep;
-    } else analysis_initial(h);
+    } else for (cur = 0; cur < nT; cur++) { T = Ts[cur]; analysis_initial(h); }
+    cur = 0; T = Ts[0];
 
     sweeps_per_megastep = (long long)(MCMegaMultiplier + 0.5);             /* MCMinorSteps = X*Y*Z*MCMoves attempts, config.c:166 */
     if (sweeps_per_megastep < 1 && MCMegaMultiplier > 0) sweeps_per_megastep = 1;
@@ -547,9 +578,12 @@ int main(int argc, char *argv[])
     for (i = 0; i < MCEqmSteps; i++) { fprintf(stderr, ","); engine_sweeps(h, sweeps_per_megastep); }   /* main.c:219-223 */
     engine_sync(h);
     if (CalculateEfield || CalculatePotential || SaveDipolesSVG) engine_gather(h);
-    if (CalculateEfield) write_efield_xyz(h, "equilib_lattice_efield.xyz", 4, 0);           /* main.c:225 */
-    if (CalculatePotential) { refresh_potential(h); write_potential_png("equilib_pot.png", Vbuf); }
-    if (SaveDipolesSVG) { SN(sn_get_lattice(h, 0, latbuf)); write_lattice_svg("equilib-SVG.svg", latbuf); }
+    for (cur = 0; cur < nT; cur++) {                                                        /* untagged files: the last T wins */
+        if (CalculateEfield) write_efield_xyz(h, "equilib_lattice_efield.xyz", 4, 0);       /* main.c:225 */
+        if (CalculatePotential) { refresh_potential(h); write_potential_png("equilib_pot.png", Vbuf); }
+        if (SaveDipolesSVG) { SN(sn_get_lattice(h, cur, latbuf)); write_lattice_svg("equilib-SVG.svg", latbuf); }
+    }
+    cur = 0;
 
     if (hyst_steps > 0 && hyst_amplitude != 0.0) {
         /* triangular ramp 0 -> +A -> -A -> 0 of Efield.x, one mega-step of sweeps per field point */
@@ -560,8 +594,8 @@ int main(int argc, char *argv[])
             float E[3] = {(float)e, (float)Efield[1], (float)Efield[2]}; double P[3];
             engine_set_efield(h, E);
             engine_sweeps(h, sweeps_per_megastep);
-            engine_polarisation(h, P);
-            fprintf(stdout, "T: %d Efield: x %f Polar: %f\n", T, e, P[0]);
+            for (cur = 0; cur < nT; cur++) { engine_polarisation(h, P); fprintf(stdout, "T: %d Efield: x %f Polar: %f\n", Ts[cur], e, P[0]); }
+            cur = 0;
         }
         { float E[3] = {(float)Efield[0], (float)Efield[1], (float)Efield[2]}; engine_set_efield(h, E); }
         fflush(stdout);
@@ -573,18 +607,22 @@ production:
         engine_sweeps(h, sweeps_per_megastep);
         engine_sync(h);
         toc = now_s();
-        analysis_midpoint(h, i, log);
+        for (cur = 0; cur < nT; cur++) { T = Ts[cur]; analysis_midpoint(h, i, logs[cur]); }
+        cur = 0; T = Ts[0];
         fflush(stdout);
         tac = now_s();
-        fprintf(stderr, "MC Moves (per second): %f MHz\n", 1e-6 * (double)sweeps_per_megastep * (double)nsites / (toc - tic));
+        fprintf(stderr, "MC Moves (per second): %f MHz\n", 1e-6 * (double)sweeps_per_megastep * (double)nsites * nT / (toc - tic));
         fprintf(stderr, "Output routines: %f s ; Efficiency of MC moves vs. analysis %.2f%%\n", tac - toc, 100.0 * (toc - tic) / (tac - tic));
         if (checkpoint_path) checkpoint_write(h, run_seed, i + 1);
     }
     fprintf(stderr, "\n");
-    engine_counters(h, &acc, &rej, &vac);
-    fprintf(stderr, "Monte Carlo moves - ACCEPT: %llu REJECT: %llu ratio: %f\n", acc, rej, (float)acc / (float)(rej + acc));
+    for (cur = 0; cur < nT; cur++) {
+        engine_counters(h, &acc, &rej, &vac);
+        if (nT > 1) fprintf(stderr, "T: %d ", Ts[cur]);
+        fprintf(stderr, "Monte Carlo moves - ACCEPT: %llu REJECT: %llu ratio: %f\n", acc, rej, (float)acc / (float)(rej + acc));
+    }
     fprintf(stderr, " For us, there is only the trying. The rest is not our business. ~T.S.Eliot\n\n");
-    if (log) fclose(log);
+    for (r = 0; r < nT; r++) if (logs[r]) fclose(logs[r]);
     SN(sn_destroy(h));
     for (i = 0; i < (ngpus > 1 ? ngpus : 0); i++) SN(sn_destroy(slab[i]));
     free(latbuf); free(Vbuf); free(slabbuf);

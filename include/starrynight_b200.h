@@ -136,6 +136,10 @@ SN_API int sn_set_counters(sn_handle *h, int replica, unsigned long long accept,
  * which is the counter word of the per-site Philox streams: a handle created with the same parameters and
  * seed, given the saved lattice and sweep count, continues the chain bit for bit.  On Z-slab handles call
  * sn_set_sweep_count on every slab before the next sn_mc_sweeps. */
+/* Give one replica its own Philox key: it then draws exactly the numbers replica 0 of a handle created with
+ * `seed` would draw, so a batch of replicas (a temperature or field sweep) reproduces as many independent
+ * runs -- the reference's only parallel mode (Makefile:49-63, one process per T, seed 0xDEADBEEF + T). */
+SN_API int sn_set_replica_seed(sn_handle *h, int replica, unsigned long long seed);
 SN_API int sn_get_sweep_count(sn_handle *h, unsigned long long *sweeps_done);
 SN_API int sn_set_sweep_count(sn_handle *h, unsigned long long sweeps_done);
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "sn_last_error", "sn_version", "sn_default_params", "sn_create", "sn_destroy", "sn_neighbour_table",
     "sn_set_lattice", "sn_get_lattice", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_mc_sweeps",
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_set_counters",
-    "sn_get_sweep_count", "sn_set_sweep_count", "sn_site_energy",
+    "sn_get_sweep_count", "sn_set_sweep_count", "sn_set_replica_seed", "sn_site_energy",
     "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_get_boundary",
     "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak",
 ]
@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     lib.sn_landau_order.argtypes = [H, C.c_int, C.POINTER(C.c_double)]
     lib.sn_rdf.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sn_set_counters.argtypes = [H, C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]
+    lib.sn_set_replica_seed.argtypes = [H, C.c_int, C.c_ulonglong]
     lib.sn_get_sweep_count.argtypes = [H, C.POINTER(C.c_ulonglong)]
     lib.sn_set_sweep_count.argtypes = [H, C.c_ulonglong]
     lib.sn_potential_map.argtypes = [H, C.c_int, C.c_void_p]
@@ -267,6 +268,9 @@ class Simulation:
         v = np.zeros(11, np.float64)
         _check(self.lib.sn_recombination(self.h, replica, v.ctypes.data))
         return v
+
+    def set_replica_seed(self, seed, replica):
+        _check(self.lib.sn_set_replica_seed(self.h, replica, int(seed)))
 
     # -- checkpoint / restart
     def sweep_count(self):

@@ -125,6 +125,7 @@ struct sn_handle {
     float *beta = nullptr;              // device, per replica
     float4 *efield = nullptr;           // device, per replica
     unsigned long long *counters = nullptr;   // device, per replica {accept, reject, vacant}
+    uint4 *rep_key = nullptr;           // device, per replica Philox key + counter tag
     unsigned long long sweep = 0;       // sweeps done so far (Philox counter word)
     cudaStream_t stream = nullptr;
     int nnb = 0;

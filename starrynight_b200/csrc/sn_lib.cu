@@ -132,6 +132,13 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
     SN_CUDA_CHECK(cudaMemsetAsync(h->lat, 0, cells * sizeof(float4), h->stream));
     SN_CUDA_CHECK(cudaMalloc(&h->beta, sizeof(float) * p->nreplicas));
     SN_CUDA_CHECK(cudaMalloc(&h->efield, sizeof(float4) * p->nreplicas));
+    SN_CUDA_CHECK(cudaMalloc(&h->rep_key, sizeof(uint4) * p->nreplicas));
+    {
+        // default streams: one key (the seed) for the handle, the replica index in the counter
+        std::vector<uint4> k(p->nreplicas);
+        for (int r = 0; r < p->nreplicas; r++) k[r] = make_uint4((uint32_t)p->seed, (uint32_t)(p->seed >> 32), (uint32_t)r << 8, 0u);
+        SN_CUDA_CHECK(cudaMemcpy(h->rep_key, k.data(), sizeof(uint4) * p->nreplicas, cudaMemcpyHostToDevice));
+    }
     SN_CUDA_CHECK(cudaMalloc(&h->counters, sizeof(unsigned long long) * 3 * p->nreplicas));
     SN_CUDA_CHECK(cudaMemsetAsync(h->counters, 0, sizeof(unsigned long long) * 3 * p->nreplicas, h->stream));
     {
@@ -181,7 +188,7 @@ extern "C" int sn_destroy(sn_handle *h)
         if (h->peer_lat[s] && !(s == 1 && h->peer_lat[1] == h->peer_lat[0])) cudaIpcCloseMemHandle(h->peer_lat[s]);
         if (h->peer_flags[s] && !(s == 1 && h->peer_flags[1] == h->peer_flags[0])) cudaIpcCloseMemHandle(h->peer_flags[s]);
     }
-    cudaFree(h->lat); cudaFree(h->beta); cudaFree(h->efield); cudaFree(h->counters); cudaFree(h->flags);
+    cudaFree(h->lat); cudaFree(h->beta); cudaFree(h->efield); cudaFree(h->counters); cudaFree(h->flags); cudaFree(h->rep_key);
     cudaFree(h->nb_table); cudaFree(h->d_nb_dxyz); cudaFree(h->d_scratch); cudaFree(h->staging);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -323,7 +330,7 @@ static SnSweepArgs sn_sweep_args(sn_handle *h)
     a.cage = (float)h->p.CageStrain; a.K = (float)h->p.K;
     a.constrain = h->p.ConstrainToX; a.dim = h->p.DIM;
     a.counters = h->counters;
-    a.key0 = (uint32_t)h->p.seed; a.key1 = (uint32_t)(h->p.seed >> 32);
+    a.rep_key = h->rep_key;
     a.sweep_lo = (uint32_t)h->sweep; a.sweep_hi = (uint32_t)(h->sweep >> 32);
     a.nb = h->nb_table; a.nnb = h->nnb;
     a.peer_lo = h->peer_lat[0]; a.peer_hi = h->peer_lat[1];
@@ -417,6 +424,15 @@ extern "C" int sn_reset_counters(sn_handle *h)
 __global__ void sn_fill_u32_kernel(unsigned int *p, long long n, unsigned int v)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+extern "C" int sn_set_replica_seed(sn_handle *h, int replica, unsigned long long seed)
+{
+    SN_CHECK_HANDLE(h, replica);
+    const uint4 k = make_uint4((uint32_t)seed, (uint32_t)(seed >> 32), 0u, 0u);     // = replica 0 of a handle created with this seed
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->rep_key + replica, &k, sizeof k, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return SN_OK;
 }
 
 extern "C" int sn_get_sweep_count(sn_handle *h, unsigned long long *sweeps)

@@ -21,7 +21,7 @@ struct SnSweepArgs {
     float cage, K;
     int constrain, dim;
     unsigned long long *counters;   // per replica {accept, reject, vacant}
-    uint32_t key0, key1;
+    const uint4 *rep_key;           // per replica: Philox key (x, y) and the tag xor-ed into counter word 1 (z)
     uint32_t sweep_lo, sweep_hi;
     const SnNbEntry *nb;
     int nnb;
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(128) sn_colour_pass_kernel(const SnSweepArgs a
             t.E = make_float3(E.x, E.y, E.z);
             t.constrain = a.constrain; t.dim = a.dim;
             const unsigned long long gsite = ((unsigned long long)x * a.G.Y + y) * a.G.Z + (a.G.z0 + z);
-            const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ ((uint32_t)rep << 8),
-                                               a.sweep_lo, a.sweep_hi, a.key0, a.key1);
+            const uint4 key = a.rep_key[rep];
+            const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ key.z, a.sweep_lo, a.sweep_hi, key.x, key.y);
             const float3 np = sn_propose(t, sn_u01(r.x), sn_u01(r.y));
             const float dE = sn_delta_e(old, np, F, Gc, t);
             accepted = sn_accept(dE, t.beta, sn_u01(r.z));

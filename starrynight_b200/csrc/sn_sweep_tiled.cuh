@@ -476,6 +476,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         tm.cage = a.cage; tm.K = a.K; tm.beta = a.beta[rep];
         { const float4 E = a.efield[rep]; tm.E = make_float3(E.x, E.y, E.z); }
         tm.constrain = a.constrain; tm.dim = a.dim;
+        const uint4 rkey = a.rep_key[rep];
         // a.lat / a.peer_* are the z-de-interleaved copies here (layout sn_pidx2)
         const long long rs2 = sn_rep_stride2(G);
         float4 *glat = a.lat + (long long)rep * rs2;
@@ -488,8 +489,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         auto draw = [&](int sp) {
             const int gx = x0 + (sp >> 2) + 4 * i, gy = y0 + (sp & 3) + 4 * j, gz = z0 + 4 * k + 2 * h;
             const unsigned long long gsite = ((unsigned long long)gx * G.Y + gy) * G.Z + (G.z0 + gz);
-            const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ ((uint32_t)rep << 8),
-                                               sweep_lo, sweep_hi, a.key0, a.key1);
+            const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ rkey.z, sweep_lo, sweep_hi, rkey.x, rkey.y);
             const uint32_t wa[2] = {r.x, r.z}, wb[2] = {r.y, r.w};
             float4 *dst = xP + (sp & 1) * 2 * snt::SITE_THREADS + tl;
 #pragma unroll

@@ -186,3 +186,33 @@ def test_driver_checkpoint_restart_continues_the_chain(built, tmp_path, shape):
             assert (runs["full"][0] / fn).read_bytes() == (runs["resumed"][0] / fn).read_bytes(), fn
     assert not (runs["resumed"][0] / "T_0300_1_001_potential.xyz").exists()      # resumed at mega-step 2
     assert runs["full"][1] == runs["resumed"][1]                                   # counters carried over
+
+
+@pytest.mark.gpu
+def test_driver_temperature_batch_equals_separate_runs(built, tmp_path):
+    """Temperatures = [...]: all T as replicas of one handle; every T-tagged file equals the one a separate
+    run at that T (argv[1], main.c:142-146) writes."""
+    cfg = ref_files()["starrynight.cfg"].decode()
+    cfg = cfg.replace("X=20", "X=16").replace("Y=20", "Y=12").replace("Z=28", "Z=12").replace('"antiferro_wall"', '"random"')
+    cfg = cfg.replace("MCMegaSteps: 1", "MCMegaSteps: 2").replace("CalculateRecombination: false", "CalculateRecombination: true")
+    temps = [150, 300, 450]
+    b = tmp_path / "batch"
+    b.mkdir()
+    (b / "starrynight.cfg").write_text(cfg + "\nTemperatures = [" + ", ".join(map(str, temps)) + "];\n")
+    run = subprocess.run([DRIVER], cwd=b, capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr[-2000:]
+    assert "Temperature batch: 3 replicas" in run.stderr
+    for T in temps:
+        d = tmp_path / f"T{T}"
+        d.mkdir()
+        (d / "starrynight.cfg").write_text(cfg)
+        one = subprocess.run([DRIVER, str(T)], cwd=d, capture_output=True, text=True)
+        assert one.returncode == 0, one.stderr[-2000:]
+        tagged = [fn for fn in sorted(os.listdir(d)) if fn.startswith(f"T_{T:04d}_")]
+        assert len(tagged) >= 8
+        for fn in tagged:
+            assert (d / fn).read_bytes() == (b / fn).read_bytes(), fn
+        strip = lambda t: [l for l in t.splitlines() if not l.startswith("#")]          # header carries time(NULL)
+        assert strip((d / f"Recombination_T_{T:04d}.log").read_text()) == strip((b / f"Recombination_T_{T:04d}.log").read_text())
+        acc = [l for l in one.stderr.splitlines() if "ACCEPT:" in l][0]
+        assert f"T: {T} {acc}" in run.stderr

@@ -208,3 +208,28 @@ def test_dataflow_launch_equals_barrier_separated_phases(sn, shape, reps, calls)
         assert np.array_equal(res[0][0][r], res[1][0][r]), f"replica {r}: dataflow chain differs from the phased chain"
         assert res[0][1][r] == res[1][1][r]
         assert not np.array_equal(res[0][0][r][..., :3], lats[r][..., :3])
+
+
+@pytest.mark.parametrize("shape", [(20, 20, 28), (32, 32, 64), (24, 24, 1)])
+def test_seeded_replicas_reproduce_independent_runs(sn, shape):
+    """sn_set_replica_seed: a batch of replicas (a temperature sweep) draws exactly the numbers of as many
+    separate handles -- the reference's parallel mode is one process per T seeded 0xDEADBEEF + T
+    (main.c:172, Makefile:49-63)."""
+    X, Y, Z = shape
+    temps = [75, 300, 450]
+    lats = [oa.random_lattice(X, Y, Z, seed=40 + r, lengths=(1.0, 0.5), prevalence=(0.8, 0.2)) for r in range(3)]
+    with sn.Simulation(X, Y, Z, CageStrain=1.0, nreplicas=3, seed=0xDEADBEEF + temps[0]) as batch:
+        for r, T in enumerate(temps):
+            batch.set_lattice(lats[r], r)
+            batch.set_T(T, r)
+            batch.set_replica_seed(0xDEADBEEF + T, r)
+        batch.MC_sweeps(2)
+        batch.MC_sweeps(3)
+        got = [(batch.get_lattice(r), batch.counters(r)) for r in range(3)]
+    for r, T in enumerate(temps):
+        with sn.Simulation(X, Y, Z, CageStrain=1.0, seed=0xDEADBEEF + T) as one:
+            one.set_lattice(lats[r])
+            one.set_T(T)
+            one.MC_sweeps(5)
+            assert np.array_equal(one.get_lattice(), got[r][0]), f"replica {r} (T={T}) differs from its separate run"
+            assert one.counters() == got[r][1]
