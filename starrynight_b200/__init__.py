@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SN_B200_LIB", os.path.join(_HERE, "libstarrynight_b200.so"))   # override: kernel experiments only
 
 SN_PREC_F32, SN_PREC_F64, SN_PREC_REPLICA = 0, 1, 2
-SN_KERNEL_AUTO, SN_KERNEL_COLOUR, SN_KERNEL_TILED, SN_KERNEL_TILED_PHASED = 0, 1, 2, 3
+SN_KERNEL_AUTO, SN_KERNEL_COLOUR, SN_KERNEL_TILED, SN_KERNEL_TILED_PHASED, SN_KERNEL_RESIDENT = 0, 1, 2, 3, 4
 SN_RDF_BINS = 81
 
 EXPORTS = [

@@ -138,6 +138,7 @@ struct sn_handle {
     bool species = true;                // false when every length is exactly 1 (skips the l_j multiplies)
     std::vector<char> rep_species;      // per replica: some length != 1
     bool use_tiled = false;
+    bool use_resident = false;          // lattice small enough to live in one CTA's shared memory (sn_sweep_resident.cuh)
     // The tiled kernel works on a second copy of the lattice whose z axis is de-interleaved by 4
     // (layout SnGeom2), so that one TMA row is 7 consecutive float4.  `lat` (canonical) and `lat2` are
     // synchronised lazily: whoever needs one of them converts from the other if it is stale.
@@ -161,6 +162,7 @@ struct sn_handle {
 // entry points implemented across translation units
 int sn_sweep_colour_launch(sn_handle *h, long long nsweeps, long long *launches);
 int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches);
+int sn_sweep_resident_launch(sn_handle *h, long long nsweeps, long long *launches);
 bool sn_tiled_supported(const sn_handle *h, std::string *why);
 int sn_tiled_prepare(sn_handle *h);
 void sn_tiled_release(sn_handle *h);

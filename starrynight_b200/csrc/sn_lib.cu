@@ -15,6 +15,7 @@
 #include "sn_observables.cuh"
 #include "sn_sweep_colour.cuh"
 #include "sn_sweep_tiled.cuh"
+#include "sn_sweep_resident.cuh"
 
 static thread_local char sn_err[512] = "";
 static int sn_slab_phase_sync(sn_handle *h, long long *launches);
@@ -172,7 +173,16 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
         sn_destroy(h);
         return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: tiled kernel unavailable: %s", why.c_str());
     }
-    h->use_tiled = can_tile && p->kernel != SN_KERNEL_COLOUR;
+    h->use_tiled = can_tile && p->kernel != SN_KERNEL_COLOUR && p->kernel != SN_KERNEL_RESIDENT;
+    {
+        std::string why_r;
+        const bool can_reside = sn_resident_supported(h, &why_r);
+        if (p->kernel == SN_KERNEL_RESIDENT && !can_reside) {
+            sn_destroy(h);
+            return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: shared-memory-resident kernel unavailable: %s", why_r.c_str());
+        }
+        h->use_resident = can_reside && !h->use_tiled && (p->kernel == SN_KERNEL_AUTO || p->kernel == SN_KERNEL_RESIDENT);
+    }
     if (h->use_tiled) { int rc = sn_tiled_prepare(h); if (rc) { sn_destroy(h); return rc; } }
     *out = h;
     return SN_OK;
@@ -370,6 +380,7 @@ static int sn_sweeps_impl(sn_handle *h, long long nsweeps, long long *launches)
     if (nsweeps < 0) return sn_fail(SN_ERR_INVALID, "sn_mc_sweeps: nsweeps %lld", nsweeps);
     if (!h->G.periodic_z && (!h->peer_lat[0] || !h->peer_lat[1]))
         return sn_fail(SN_ERR_INVALID, "sn_mc_sweeps: Z-slab handle has no neighbours attached (sn_ipc_attach / sn_attach_peer)");
+    if (h->use_resident) return sn_sweep_resident_launch(h, nsweeps, launches);
     return h->use_tiled ? sn_sweep_tiled_launch(h, nsweeps, launches) : sn_sweep_colour_launch(h, nsweeps, launches);
 }
 

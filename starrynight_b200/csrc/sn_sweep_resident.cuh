@@ -1,0 +1,191 @@
+// sn_sweep_resident.cuh -- Metropolis sweeps of a lattice that lives in shared memory.
+//
+// Replaces MC_moves -> MC_move -> site_energy (montecarlo-core.c:76-191) for lattices of up to
+// ~14 000 sites (X*Y*Z*16 B <= 227 KB): the 2-D 100x100 case of the reference's figures, its
+// `make test` 20x20x28 lattice, and the small 3-D lattices of temperature / field sweeps, usually
+// batched as replicas.  One CTA owns one replica: it loads the lattice into shared memory once,
+// runs EVERY sweep of the sn_mc_sweeps call there -- all colour sublattices back to back with a
+// block barrier between them instead of a kernel launch -- and writes the lattice back once.  HBM
+// sees 32 B per site per call instead of ~2 KB per site per sweep, and there are no launch gaps
+// (the colour-pass kernel needs 16-64 launches per sweep, each a few microseconds of mostly
+// latency at this size).
+//
+// Same colour order, same Philox streams and the same arithmetic (sn_local_field_*, sn_delta_e)
+// as sn_colour_pass_kernel, so the chain is bit-identical to it; the periodic wrap that the
+// padded global array resolves with ghost cells is resolved here by per-axis offset tables.
+#pragma once
+
+#include "sn_sweep_colour.cuh"
+
+namespace snr {
+constexpr int MAX_SMEM = 227 * 1024;
+__host__ __device__ constexpr int threads(int mode) { return mode == 1 ? 640 : 256; }   // 2-D: 625 sites per colour at 100x100
+
+// Shared-memory layout.  Threads of a colour pass own sites P = cutoff + 1 apart along the innermost
+// interacting axis (z, or y when Z == 1); stored naively their float4 would sit 64 B apart and every
+// LDS.128 of a warp would take 4x the wavefronts.  That axis is therefore de-interleaved by P: coordinate
+// v lives at (v % P) * ceil(n / P) + v / P, so the lanes of a pass read consecutive float4.  Per-axis
+// tables (built once per CTA) hold the element offset of every coordinate -cutoff .. n + cutoff - 1 with
+// the periodic wrap already applied; a neighbour address is three table entries added up.
+struct Layout {
+    int Py, Qy, Pz, Qz;     // de-interleave period and run length of y and z (period 1 = plain)
+    int sX, sY;             // element strides
+    int cells;              // float4 slots of the tile (>= X*Y*Z when an extent is not a multiple of P)
+    int g;                  // table margin = cutoff
+    int tab_off;            // byte offset of the tables behind the tile
+};
+__host__ __device__ inline Layout layout(const SnGeom &G, int cutoff, int Pinner)
+{
+    Layout L;
+    L.g = cutoff;
+    if (G.Z > 1) { L.Pz = Pinner; L.Qz = (G.nz + Pinner - 1) / Pinner; L.Py = 1; L.Qy = G.Y; }
+    else { L.Py = Pinner; L.Qy = (G.Y + Pinner - 1) / Pinner; L.Pz = 1; L.Qz = 1; }
+    L.sY = L.Pz * L.Qz; L.sX = L.Py * L.Qy * L.sY;
+    L.cells = G.X * L.sX;
+    L.tab_off = L.cells * 16;
+    return L;
+}
+__host__ __device__ inline int smem_bytes(const SnGeom &G, const Layout &L) { return L.tab_off + 4 * (G.X + G.Y + G.nz + 6 * L.g); }
+}
+
+template <int MODE, bool SPECIES>
+__global__ void __launch_bounds__(snr::threads(MODE), 1)
+sn_resident_kernel(const SnSweepArgs a, const snr::Layout L, const int nrep, const unsigned long long sweep0, const int nsweeps)
+{
+    extern __shared__ __align__(16) unsigned char sn_resident_smem[];
+    float4 *tile = reinterpret_cast<float4 *>(sn_resident_smem);
+    const SnGeom &G = a.G;
+    const int X = G.X, Y = G.Y, Z = G.nz, N = X * Y * Z, tid = threadIdx.x, nthr = blockDim.x, g = L.g;
+    int *xtab = reinterpret_cast<int *>(sn_resident_smem + L.tab_off), *ytab = xtab + X + 2 * g, *ztab = ytab + Y + 2 * g;
+    auto wrapn = [](int v, int n) { v %= n; return v < 0 ? v + n : v; };
+    for (int i = tid; i < X + 2 * g; i += nthr) xtab[i] = wrapn(i - g, X) * L.sX;
+    for (int i = tid; i < Y + 2 * g; i += nthr) { const int y = wrapn(i - g, Y); ytab[i] = ((y % L.Py) * L.Qy + y / L.Py) * L.sY; }
+    for (int i = tid; i < Z + 2 * g; i += nthr) { const int z = wrapn(i - g, Z); ztab[i] = (z % L.Pz) * L.Qz + z / L.Pz; }
+    __syncthreads();
+
+    for (int rep = blockIdx.x; rep < nrep; rep += gridDim.x) {
+        float4 *lat = a.lat + (long long)rep * G.rep_stride;
+        for (int i = tid; i < N; i += nthr) {
+            const int z = i % Z, y = (i / Z) % Y, x = i / (Z * Y);
+            tile[xtab[x + g] + ytab[y + g] + ztab[z + g]] = lat[sn_pidx(G, x, y, z)];
+        }
+        __syncthreads();
+
+        SnTerms t;
+        t.cage = a.cage; t.K = a.K; t.beta = a.beta[rep];
+        { const float4 E = a.efield[rep]; t.E = make_float3(E.x, E.y, E.z); }
+        t.constrain = a.constrain; t.dim = a.dim;
+        const uint4 key = a.rep_key[rep];
+        int n_acc = 0, n_rej = 0, n_vac = 0;
+
+        for (int s = 0; s < nsweeps; s++) {
+            const unsigned long long sw = sweep0 + (unsigned long long)s;
+            const uint32_t sweep_lo = (uint32_t)sw, sweep_hi = (uint32_t)(sw >> 32);
+            for (int cx = 0; cx < a.ax.ncol; cx++) for (int cy = 0; cy < a.ay.ncol; cy++) for (int cz = 0; cz < a.az.ncol; cz++) {
+                const int nx = sn_axis_count(a.ax, cx), ny = sn_axis_count(a.ay, cy), nz = sn_axis_count(a.az, cz);
+                const int total = nx * ny * nz;
+                for (int idx = tid; idx < total; idx += nthr) {
+                    const int k = idx % nz, j = (idx / nz) % ny, i = idx / (nz * ny);
+                    const int x = sn_axis_coord(a.ax, cx, i), y = sn_axis_coord(a.ay, cy, j), z = sn_axis_coord(a.az, cz, k);
+                    const int c = xtab[x + g] + ytab[y + g] + ztab[z + g];
+                    const float4 old = tile[c];
+                    if (old.w == 0.0f) { n_vac++; continue; }                     // montecarlo-core.c:163
+                    float3 F = make_float3(0.f, 0.f, 0.f), Gc = make_float3(0.f, 0.f, 0.f);
+                    if constexpr (MODE == 2) {
+                        const int *xt = xtab + x + g, *yt = ytab + y + g, *zt = ztab + z + g;
+                        auto load = [&](int dx, int dy, int dz) { return tile[xt[dx] + yt[dy] + zt[dz]]; };
+                        sn_local_field_table(a.nb, a.nnb, load, F, Gc);
+                    } else {
+                        // element offsets of the 7 (wrapped) coordinates per axis: registers after unrolling
+                        int xa[7], ya[7], za[7];
+#pragma unroll
+                        for (int d = 0; d < 7; d++) {
+                            xa[d] = xtab[x + d]; ya[d] = ytab[y + d];
+                            za[d] = MODE == 1 ? 0 : ztab[z + d];
+                        }
+                        auto load = [&](int dx, int dy, int dz) { return tile[xa[dx + 3] + ya[dy + 3] + za[dz + 3]]; };
+                        sn_local_field_cut3<MODE == 1, SPECIES>(load, F, Gc);
+                    }
+                    const unsigned long long gsite = ((unsigned long long)x * G.Y + y) * G.Z + (G.z0 + z);
+                    const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ key.z, sweep_lo, sweep_hi, key.x, key.y);
+                    const float3 np = sn_propose(t, sn_u01(r.x), sn_u01(r.y));
+                    const float dE = sn_delta_e(old, np, F, Gc, t);
+                    const bool accepted = sn_accept(dE, t.beta, sn_u01(r.z));
+                    if (accepted) tile[c] = make_float4(np.x, np.y, np.z, old.w);
+                    n_acc += accepted; n_rej += !accepted;
+                }
+                __syncthreads();
+            }
+        }
+
+        for (int i = tid; i < N; i += nthr) {
+            const int z = i % Z, y = (i / Z) % Y, x = i / (Z * Y);
+            lat[sn_pidx(G, x, y, z)] = tile[xtab[x + g] + ytab[y + g] + ztab[z + g]];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+            n_rej += __shfl_xor_sync(0xffffffffu, n_rej, o);
+            n_vac += __shfl_xor_sync(0xffffffffu, n_vac, o);
+        }
+        if ((tid & 31) == 0) {
+            unsigned long long *cnt = a.counters + 3 * rep;
+            if (n_acc) atomicAdd(cnt + 0, (unsigned long long)n_acc);
+            if (n_rej) atomicAdd(cnt + 1, (unsigned long long)n_rej);
+            if (n_vac) atomicAdd(cnt + 2, (unsigned long long)n_vac);
+        }
+        __syncthreads();                                  // the tile is reused by the CTA's next replica
+    }
+}
+
+// ---- host side -------------------------------------------------------------------
+bool sn_resident_supported(const sn_handle *h, std::string *why)
+{
+    const SnGeom &G = h->G;
+    const int g = h->p.cutoff;
+    const char *msg = nullptr;
+    if (!G.periodic_z) msg = "Z-slab handle";
+    else if ((long long)G.X * G.Y * G.Z * 16 > snr::MAX_SMEM ||
+             snr::smem_bytes(G, snr::layout(G, g, sn_axis_colour(G.Z > 1 ? G.Z : G.Y, g, false).P)) > snr::MAX_SMEM)
+        msg = "lattice does not fit in 227 KB of shared memory";
+    else if (G.X < g || G.Y < g || (G.Z > 1 && G.Z < g)) msg = "an extent is smaller than DipoleCutOff";
+    if (msg) { if (why) *why = msg; return false; }
+    return true;
+}
+
+template <int MODE, bool SPECIES>
+static int sn_resident_launch_t(sn_handle *h, const SnSweepArgs &a, long long nsweeps)
+{
+    const snr::Layout L = snr::layout(h->G, h->p.cutoff, h->G.Z > 1 ? a.az.P : a.ay.P);
+    const int smem = snr::smem_bytes(h->G, L);
+    auto kern = sn_resident_kernel<MODE, SPECIES>;
+    SN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = std::min(h->p.nreplicas, h->num_sms);
+    long long done = 0;
+    while (done < nsweeps) {                              // the kernel's sweep count is an int
+        const int chunk = (int)std::min<long long>(nsweeps - done, 1 << 30);
+        kern<<<grid, snr::threads(MODE), smem, h->stream>>>(a, L, h->p.nreplicas, h->sweep + (unsigned long long)done, chunk);
+        done += chunk;
+    }
+    SN_CUDA_CHECK(cudaGetLastError());
+    return SN_OK;
+}
+
+int sn_sweep_resident_launch(sn_handle *h, long long nsweeps, long long *launches)
+{
+    if (nsweeps <= 0) return SN_OK;
+    { int rc = sn_sync_canonical(h); if (rc) return rc; }
+    h->lat2_valid = false;
+    const SnSweepArgs a = sn_sweep_args(h);
+    const int mode = h->p.cutoff == 3 ? (h->p.Z == 1 ? 1 : 0) : 2;
+    int rc;
+    if (mode == 0) rc = h->species ? sn_resident_launch_t<0, true>(h, a, nsweeps) : sn_resident_launch_t<0, false>(h, a, nsweeps);
+    else if (mode == 1) rc = h->species ? sn_resident_launch_t<1, true>(h, a, nsweeps) : sn_resident_launch_t<1, false>(h, a, nsweeps);
+    else rc = sn_resident_launch_t<2, true>(h, a, nsweeps);
+    if (rc) return rc;
+    h->sweep += (unsigned long long)nsweeps;
+    if (launches) *launches += (nsweeps + (1LL << 30) - 1) >> 30;
+    if ((rc = sn_refresh_ghosts(h))) return rc;           // the kernel wrote interior cells only
+    if (launches) (*launches)++;
+    return SN_OK;
+}

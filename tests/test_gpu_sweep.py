@@ -233,3 +233,46 @@ def test_seeded_replicas_reproduce_independent_runs(sn, shape):
             one.MC_sweeps(5)
             assert np.array_equal(one.get_lattice(), got[r][0]), f"replica {r} (T={T}) differs from its separate run"
             assert one.counters() == got[r][1]
+
+
+RESIDENT_CASES = [
+    # X, Y, Z, cutoff, K, ConstrainToX, DIM, replicas
+    (20, 20, 28, 3, 0.0, False, 3, 2),          # the reference's `make test` lattice
+    (100, 100, 1, 3, 0.0, False, 3, 3),         # the 2-D figures case
+    (13, 17, 11, 3, 0.6, False, 3, 1),          # odd extents: extra colours on every axis
+    (9, 11, 10, 2, 0.0, False, 3, 2),           # table-driven cut-offs
+    (9, 10, 9, 4, 0.3, True, 3, 1),
+    (12, 12, 12, 3, 0.0, False, 2, 1),
+    (24, 24, 1, 3, 0.0, False, 3, 1),
+    (8, 8, 8, 3, 0.0, False, 3, 200),           # more replicas than SMs: CTAs loop over replicas
+    (4, 5, 3, 3, 0.0, False, 3, 2),             # extents barely above the cut-off
+]
+
+
+@pytest.mark.parametrize("case", RESIDENT_CASES)
+def test_resident_kernel_equals_colour_passes_bit_for_bit(sn, case):
+    """The shared-memory-resident kernel runs the same colour order, Philox streams and arithmetic as one
+    launch per colour over global memory: identical lattices and counters, any sweeps per call."""
+    X, Y, Z, cut, K, constrain, dim, reps = case
+    lats = [oa.random_lattice(X, Y, Z, seed=60 + r % 5, lengths=(1.0, 0.5, 0.0), prevalence=(0.7, 0.2, 0.1)) for r in range(reps)]
+    res = []
+    for kern in (sn.SN_KERNEL_RESIDENT, sn.SN_KERNEL_COLOUR):
+        with sn.Simulation(X, Y, Z, DipoleCutOff=cut, CageStrain=1.0, K=K, Efield=(0.02, 0.01, 0), ConstrainToX=constrain, DIM=dim,
+                           nreplicas=reps, seed=31, kernel=kern) as sim:
+            for r in range(reps):
+                sim.set_lattice(lats[r], r)
+                sim.set_T(100 + 37 * (r % 11), r)
+            sim.MC_sweeps(3)
+            sim.MC_sweeps(1)
+            e = sim.total_energy(sn.SN_PREC_F64, reps - 1)          # through the ghost shell the kernel left behind
+            res.append(([sim.get_lattice(r) for r in range(reps)], [sim.counters(r) for r in range(reps)], e))
+    for r in range(reps):
+        assert np.array_equal(res[0][0][r], res[1][0][r]), f"replica {r}"
+        assert res[0][1][r] == res[1][1][r]
+    assert np.array_equal(res[0][2], res[1][2])
+    assert not np.array_equal(res[0][0][0][..., :3], lats[0][..., :3])
+
+
+def test_resident_kernel_refuses_what_it_cannot_hold(sn):
+    with pytest.raises(sn.SnError, match="shared memory"):
+        sn.Simulation(32, 32, 32, kernel=sn.SN_KERNEL_RESIDENT)
