@@ -276,3 +276,112 @@ def test_resident_kernel_equals_colour_passes_bit_for_bit(sn, case):
 def test_resident_kernel_refuses_what_it_cannot_hold(sn):
     with pytest.raises(sn.SnError, match="shared memory"):
         sn.Simulation(32, 32, 32, kernel=sn.SN_KERNEL_RESIDENT)
+
+
+def test_tiled_kernel_statistics_match_colour_passes(sn):
+    """The tiled dataflow kernel and the colour-pass kernel are different update orders of the same Markov
+    kernel with the same stationary distribution: equilibrium energy, field-induced polarisation and
+    acceptance agree within error bars (8 independent replicas each, 32^3, T = 300 K, E_x = 0.3)."""
+    X, R = 32, 8
+    lat0 = oa.random_lattice(X, X, X, seed=71)
+    stats = {}
+    for name, kern in (("tiled", sn.SN_KERNEL_TILED), ("colour", sn.SN_KERNEL_COLOUR)):
+        with sn.Simulation(X, X, X, CageStrain=1.0, Efield=(0.3, 0, 0), beta=1.0, nreplicas=R, seed=900 + len(name), kernel=kern) as sim:
+            for r in range(R):
+                sim.set_lattice(lat0, r)
+            sim.MC_sweeps(80)
+            sim.reset_counters()
+            es, ps = np.zeros((R, 25)), np.zeros((R, 25))
+            for k in range(25):
+                sim.MC_sweeps(4)
+                for r in range(R):
+                    es[r, k] = sim.total_energy(sn.SN_PREC_F32, r).sum() / X ** 3
+                    ps[r, k] = sim.polarisation(r)[0]
+            acc = np.array([sim.counters(r)[0] / sum(sim.counters(r)[:2]) for r in range(R)])
+        stats[name] = np.stack([es.mean(1), ps.mean(1), acc], 1)
+    for col, what in enumerate(("energy per site", "polarisation", "acceptance ratio")):
+        a, b = stats["tiled"][:, col], stats["colour"][:, col]
+        se = np.sqrt(a.var(ddof=1) / R + b.var(ddof=1) / R)
+        assert abs(a.mean() - b.mean()) < 4.5 * se + 1e-4, f"{what}: tiled {a.mean():.5f} vs colour {b.mean():.5f} (se {se:.5f})"
+
+
+def test_correlation_functions_match_reference_chain(sn):
+    """radial_order_parameter at equilibrium (T = 150 K): the nearest shells' FE and AFE correlations from the
+    GPU chain vs the reference's serial chain (oracle f32), independent seeds, 4.5 combined standard errors."""
+    X, T = 10, 150
+    p = oa.make_params(X, X, X, 3, 1.0, 0.0, (0.0, 0.0, 0.0), 1.0 / (T / 300.0))
+    lat0 = oa.random_lattice(X, X, X, seed=13)
+    o = oa.Oracle("f32")
+    n, eqm, nsamp, stride, shells = X ** 3, 100, 12, 5, [1, 2, 3, 4]
+    ref = []
+    for s in range(200, 205):
+        lat = np.ascontiguousarray(lat0, np.float32)
+        mt = o.mt(s)
+        o.mc_moves(p, lat, mt, eqm * n)
+        acc_fe, acc_afe = np.zeros(4), np.zeros(4)
+        for _ in range(nsamp):
+            o.mc_moves(p, lat, mt, stride * n)
+            fe, afe, cnt = o.rdf(p, lat)
+            acc_fe += np.asarray(fe, np.float64)[shells] / cnt[shells]
+            acc_afe += np.asarray(afe, np.float64)[shells] / cnt[shells]
+        ref.append(np.concatenate([acc_fe, acc_afe]) / nsamp)
+    ref = np.array(ref)
+    R = 12
+    with sim_for(sn, p, nreplicas=R, seed=5151) as sim:
+        for r in range(R):
+            sim.set_lattice(lat0, r)
+        sim.MC_sweeps(eqm)
+        gpu = np.zeros((R, 8))
+        for _ in range(nsamp):
+            sim.MC_sweeps(stride)
+            for r in range(R):
+                fe, afe, cnt = sim.radial_order_parameter(r)
+                gpu[r, :4] += fe[shells] / cnt[shells]
+                gpu[r, 4:] += afe[shells] / cnt[shells]
+        gpu /= nsamp
+    for c in range(8):
+        se = np.sqrt(ref[:, c].var(ddof=1) / len(ref) + gpu[:, c].var(ddof=1) / R)
+        what = ("FE", "AFE")[c // 4] + f" correlation at r^2={shells[c % 4]}"
+        assert abs(ref[:, c].mean() - gpu[:, c].mean()) < 4.5 * se + 2e-4, f"{what}: reference {ref[:, c].mean():.5f} vs GPU {gpu[:, c].mean():.5f} (se {se:.5f})"
+
+
+def test_hysteresis_loop_matches_reference_chain(sn):
+    """The field protocol main.c:229-238 sketches (commented out there; `Hysteresis` in our driver): a triangular
+    ramp of Efield.x with a fixed number of sweeps per field point.  Polarisation at every point of the loop,
+    GPU replicas vs the reference's serial chain driven through the same protocol, within error bars."""
+    X, T, A, steps, spp = 8, 200, 0.6, 4, 6
+    beta = 1.0 / (T / 300.0)
+    fields = [A * (ph if ph < 1 else 2 - ph if ph < 3 else ph - 4) for ph in (s / steps for s in range(4 * steps))]
+    lat0 = oa.random_lattice(X, X, X, seed=14)
+    o = oa.Oracle("f32")
+    n = X ** 3
+    ref = []
+    for s in range(300, 310):
+        lat = np.ascontiguousarray(lat0, np.float32)
+        mt = o.mt(s)
+        o.mc_moves(oa.make_params(X, X, X, 3, 1.0, 0.0, (0.0, 0.0, 0.0), beta), lat, mt, 40 * n)
+        row = []
+        for e in fields:
+            p = oa.make_params(X, X, X, 3, 1.0, 0.0, (float(np.float32(e)), 0.0, 0.0), beta)
+            o.mc_moves(p, lat, mt, spp * n)
+            row.append(o.polarisation(p, lat))
+        ref.append(row)
+    ref = np.array(ref)
+    R = 24
+    with sn.Simulation(X, X, X, CageStrain=1.0, beta=beta, nreplicas=R, seed=6161) as sim:
+        for r in range(R):
+            sim.set_lattice(lat0, r)
+        sim.MC_sweeps(40)
+        gpu = np.zeros((R, len(fields)))
+        for k, e in enumerate(fields):
+            for r in range(R):
+                sim.set_efield((e, 0, 0), r)
+            sim.MC_sweeps(spp)
+            for r in range(R):
+                gpu[r, k] = sim.polarisation(r)[0]
+    for k, e in enumerate(fields):
+        se = np.sqrt(ref[:, k].var(ddof=1) / len(ref) + gpu[:, k].var(ddof=1) / R)
+        assert abs(ref[:, k].mean() - gpu[:, k].mean()) < 4.5 * se + 2e-3, f"E_x={e:+.2f} (point {k}): reference {ref[:, k].mean():.4f} vs GPU {gpu[:, k].mean():.4f} (se {se:.4f})"
+    up, down = gpu[:, steps].mean(), gpu[:, 3 * steps].mean()
+    # the loop polarises both ways; the reference's field term is +p.E (montecarlo-core.c:120-123), so P opposes E
+    assert up < -0.05 and down > 0.05
