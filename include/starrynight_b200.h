@@ -193,7 +193,10 @@ SN_API int sn_set_ghost(sn_handle *h, int replica, int side, const float *planes
 SN_API int sn_ipc_export(sn_handle *h, void *lattice_handle64, void *flags_handle64);
 /* attach the neighbour that owns the planes below (side 0) / above (side 1) */
 SN_API int sn_ipc_attach(sn_handle *h, int side, const void *lattice_handle64, const void *flags_handle64);
-/* same wiring for two handles living in one process (peer access is enabled) */
+/* same wiring for two handles living in one process (peer access is enabled).  Slabs of one lattice wait for each
+ * other from inside their persistent sweep kernels, so they must be able to run at the same time: one slab per GPU
+ * is the intended layout; several slab handles of one process on the same device share its SMs equally (handles in
+ * different processes cannot see each other: keep to one slab per GPU there). */
 SN_API int sn_attach_peer(sn_handle *h, int side, sn_handle *peer);
 
 #ifdef __cplusplus

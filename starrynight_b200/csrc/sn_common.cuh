@@ -153,6 +153,7 @@ struct sn_handle {
     bool peer_is_ipc[2] = {false, false};
     unsigned char ipc_key[2][64] = {};
     int num_sms = 148;
+    int grid_limit = 0;                 // > 0: cap on the tiled kernel's persistent grid (slab neighbours sharing this device)
     void *tmap = nullptr;               // CUtensorMap storage for the tiled kernel (device-constant copy made at launch)
     // scratch
     double *d_scratch = nullptr; size_t scratch_bytes = 0;

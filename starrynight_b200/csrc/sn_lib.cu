@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "sn_common.cuh"
 #include "sn_field.cuh"
@@ -86,6 +87,25 @@ static void sn_build_neighbours(sn_handle *h)
     cudaMemcpy(h->nb_table, tab.data(), sizeof(SnNbEntry) * h->nnb, cudaMemcpyHostToDevice);
     cudaMalloc(&h->d_nb_dxyz, sizeof(int) * 3 * std::max(1, h->nnb));
     cudaMemcpy(h->d_nb_dxyz, h->nb_dxyz.data(), sizeof(int) * 3 * h->nnb, cudaMemcpyHostToDevice);
+}
+
+// Slab handles of this process, by device.  Slabs of one lattice wait for each other's tile versions from inside
+// their persistent sweep kernels (directly or through a chain of neighbours on other devices), so all slab kernels
+// that share a device must be resident at once: one CTA per SM, hence each gets an equal share of the SMs.
+static std::mutex sn_slab_registry_mutex;
+static std::vector<sn_handle *> sn_slab_registry;
+
+static void sn_slab_register(sn_handle *h, bool add)
+{
+    std::lock_guard<std::mutex> lock(sn_slab_registry_mutex);
+    auto it = std::find(sn_slab_registry.begin(), sn_slab_registry.end(), h);
+    if (add && it == sn_slab_registry.end()) sn_slab_registry.push_back(h);
+    if (!add && it != sn_slab_registry.end()) sn_slab_registry.erase(it);
+    for (sn_handle *a : sn_slab_registry) {
+        int n = 0;
+        for (sn_handle *b : sn_slab_registry) n += b->p.device == a->p.device;
+        a->grid_limit = n > 1 ? std::max(1, a->num_sms / n) : 0;
+    }
 }
 
 static int sn_mode(const sn_handle *h) { return h->p.cutoff == 3 ? (h->p.Z == 1 ? 1 : 0) : 2; }
@@ -184,6 +204,7 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
         h->use_resident = can_reside && !h->use_tiled && (p->kernel == SN_KERNEL_AUTO || p->kernel == SN_KERNEL_RESIDENT);
     }
     if (h->use_tiled) { int rc = sn_tiled_prepare(h); if (rc) { sn_destroy(h); return rc; } }
+    if (!G.periodic_z) sn_slab_register(h, true);
     *out = h;
     return SN_OK;
 }
@@ -191,6 +212,7 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
 extern "C" int sn_destroy(sn_handle *h)
 {
     if (!h) return SN_OK;
+    if (!h->G.periodic_z) sn_slab_register(h, false);
     cudaSetDevice(h->p.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     sn_tiled_release(h);

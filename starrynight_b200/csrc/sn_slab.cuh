@@ -129,6 +129,7 @@ extern "C" int sn_attach_peer(sn_handle *h, int side, sn_handle *peer)
         cudaGetLastError();
     }
     if (peer->use_tiled != h->use_tiled) return sn_fail(SN_ERR_INVALID, "sn_attach_peer: slabs must run the same sweep kernel");
+
     h->peer_lat[side] = h->use_tiled ? peer->lat2 : peer->lat; h->peer_flags[side] = peer->flags; h->peer_is_ipc[side] = false;
     return SN_OK;
 }

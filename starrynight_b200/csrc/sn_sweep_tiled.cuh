@@ -785,7 +785,8 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
     auto launch = [&](unsigned long long n0, unsigned long long n1) -> int {
         f.n_begin = n0; f.n_end = n1;
         SN_CUDA_CHECK(cudaMemsetAsync(f.next, 0, sizeof(unsigned long long), h->stream));
-        const int grid = (int)std::min<unsigned long long>(n1 - n0, (unsigned long long)h->num_sms);
+        const int sms = h->grid_limit > 0 ? std::min(h->grid_limit, h->num_sms) : h->num_sms;
+        const int grid = (int)std::min<unsigned long long>(n1 - n0, (unsigned long long)sms);
         if (h->species) sn_tiled_kernel<true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
         else sn_tiled_kernel<false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
         if (launches) (*launches)++;

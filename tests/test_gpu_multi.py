@@ -90,3 +90,16 @@ def test_slabs_run_many_sweeps_per_launch(sn):
     assert np.array_equal(out, ref)
     assert np.array_equal(counters, ref_c)
     assert np.allclose(energy, ref_e, rtol=1e-12, atol=1e-9)
+
+
+def test_two_large_slabs_per_device_share_the_sms(sn):
+    """Two slabs of one lattice on the SAME device, each with more tiles than SMs: their persistent kernels wait for
+    each other's tile versions, so both must be resident -- sn_attach_peer halves their grids.  Still the 1-GPU chain."""
+    X, Y, Z = 256, 256, 128
+    lat = oa.random_lattice(X, Y, Z, seed=24)
+    with sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.05, 0, 0), seed=99, kernel=sn.SN_KERNEL_TILED) as one:
+        one.set_lattice(lat)
+        one.MC_sweeps(2)
+        ref = one.get_lattice()
+    out, _, _ = _run_split(sn, lat, 4, sn.SN_KERNEL_TILED, 2, devices=[0, 1], per_call=2)
+    assert np.array_equal(out, ref)
