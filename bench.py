@@ -390,6 +390,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = attempts_step * args.steps / e2e_s
+    # lattice-wide observables of the final state, merged over the slabs by one FP64 all_reduce (sanity of the run)
+    from starrynight_b200 import slab as sn_slab
+    merged = sn_slab.merge_observables(sim, dist if n > 1 else None, n, precision=sn.SN_PREC_F32)
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks = {}
@@ -430,7 +433,8 @@ def run_ours(args):
                          "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                                  "peak_source": hbm_src, "bytes_per_attempt": BYTES_PER_ATTEMPT},
                          "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write per launch, scaled by attempts per launch)"},
-            "accept_ratio": acc / max(1, acc + rej),
+            "accept_ratio": merged["accept"] / max(1, merged["accept"] + merged["reject"]),
+            "energy_per_site": float(merged["energy"].sum() / merged["nsites"]),
             "wall_s_timed_region": t_wall,
         }
         if n == 1 and not args.no_cpu_baseline:

@@ -60,3 +60,23 @@ def wire_ipc(sim, dist, world: int, rank: int):
     lo, hi = ring_neighbours(world, rank)
     sim.ipc_attach(0, *handles[lo])
     sim.ipc_attach(1, *handles[hi])
+
+
+def merge_observables(sim, dist, world: int, replica: int = 0, precision: int = 0):
+    """Lattice-wide observables of a slab-decomposed lattice from the slabs' own reductions: ONE small FP64
+    all_reduce (the only collective on this path; the sweep itself exchanges nothing through it).
+
+    Returns dict(polarisation[3] = (1/N) sum p, energy[4] = pair, cage, field, K terms, accept, reject, vacant).
+    `sim` needs polarisation(replica) -> mean over its slab, total_energy(precision, replica) -> its slab's share
+    (pair terms across a seam are counted half on each side), counters(replica) and nsites."""
+    import torch
+    P = np.asarray(sim.polarisation(replica), np.float64) * sim.nsites
+    E = np.asarray(sim.total_energy(precision, replica), np.float64)
+    c = np.asarray(sim.counters(replica), np.float64)            # exact below 2^53 attempts
+    t = torch.from_numpy(np.concatenate([P, E, c, [float(sim.nsites)]]))
+    if world > 1:
+        tt = t.cuda() if dist.get_backend() == "nccl" else t      # NCCL reduces device tensors only
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        t = tt.cpu()
+    v = t.numpy()
+    return dict(polarisation=v[0:3] / v[10], energy=v[3:7].copy(), accept=int(v[7]), reject=int(v[8]), vacant=int(v[9]), nsites=int(v[10]))

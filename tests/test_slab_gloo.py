@@ -27,6 +27,20 @@ class FakeSlab:
     def set_ghost(self, side, planes, replica=0):
         self.ghost[side] = np.array(planes, copy=True)
 
+    # observables of the own planes, same surface as Simulation
+    @property
+    def nsites(self):
+        return self.own.shape[0] * self.own.shape[1] * self.nz
+
+    def polarisation(self, replica=0):
+        return self.own[..., :3].astype(np.float64).reshape(-1, 3).mean(0)
+
+    def total_energy(self, precision=0, replica=0):
+        return np.array([self.own[..., 0].astype(np.float64).sum(), 1.0, 2.0, 0.0])
+
+    def counters(self, replica=0):
+        return (10 * self.nz, 20 * self.nz, self.nz)
+
 
 def test_slab_range_and_ring():
     assert slab.slab_range(512, 8, 3, 32) == (192, 64)
@@ -68,6 +82,10 @@ def _worker(rank, world, port, Z, out):
     below = np.take(full, [(z0 - 3 + i) % Z for i in range(3)], axis=2)
     above = np.take(full, [(z0 + nz + i) % Z for i in range(3)], axis=2)
     ok = np.array_equal(sim.ghost[0], below) and np.array_equal(sim.ghost[1], above)
+    m = slab.merge_observables(sim, dist, world)                       # one FP64 all_reduce
+    ok = ok and np.allclose(m["polarisation"], full[..., :3].astype(np.float64).reshape(-1, 3).mean(0), rtol=1e-13, atol=1e-15)
+    ok = ok and np.isclose(m["energy"][0], full[..., 0].astype(np.float64).sum(), rtol=1e-13) and m["energy"][1] == world
+    ok = ok and (m["accept"], m["reject"], m["vacant"], m["nsites"]) == (10 * Z, 20 * Z, Z, 6 * 5 * Z)
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
