@@ -216,3 +216,21 @@ def test_driver_temperature_batch_equals_separate_runs(built, tmp_path):
         assert strip((d / f"Recombination_T_{T:04d}.log").read_text()) == strip((b / f"Recombination_T_{T:04d}.log").read_text())
         acc = [l for l in one.stderr.splitlines() if "ACCEPT:" in l][0]
         assert f"T: {T} {acc}" in run.stderr
+
+
+def test_driver_extra_keys_host_logic(built, tmp_path):
+    """Host-side handling of the B200-only cfg keys (no GPU needed: --init-only stops before sn_create)."""
+    cfg = ref_files()["starrynight.cfg"].decode().replace('"antiferro_wall"', '"random"')
+    # Temperatures overrides T: the first entry seeds replica 0 exactly like `T: 310` / argv[1] = 310 would
+    a = run_init_only(tmp_path, cfg + "\nTemperatures = [310, 350];\n")
+    b = run_init_only(tmp_path, cfg.replace("T: 300", "T: 310"))
+    assert np.array_equal(a, b)
+    # combinations the driver refuses, with a message and a non-zero exit code
+    for extra in ("Temperatures = [300, 350];\nGPUs = 2;", 'Temperatures = [300, 350];\nCheckpoint = "c.bin";', "GPUs = 0;", "GPUs = 99;"):
+        (tmp_path / "starrynight.cfg").write_text(cfg + "\n" + extra + "\n")
+        bad = subprocess.run([DRIVER, "--init-only", "x.bin"], cwd=tmp_path, capture_output=True, text=True)
+        assert bad.returncode != 0 and ("Temperatures" in bad.stderr or "GPUs" in bad.stderr), extra
+    # a restart file that does not match the configuration is refused before any GPU work
+    (tmp_path / "starrynight.cfg").write_text(cfg + '\nRestart = "nope.bin";\n')
+    bad = subprocess.run([DRIVER], cwd=tmp_path, capture_output=True, text=True)
+    assert bad.returncode != 0 and "Restart" in bad.stderr
