@@ -45,12 +45,15 @@ def run(name, X, Y, Z, reps, sweeps, temps=None, **kw):
     return row
 
 rows = []
+QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"
 rows.append(run("C2 100x100x1 Efield.x=0.02, 64 replicas", 100, 100, 1, 64, 200, Efield=(0.02, 0, 0)))
 rows.append(run("C2 100x100x1 Efield.x=0.02, 1024 replicas", 100, 100, 1, 1024, 50, Efield=(0.02, 0, 0)))
 rows.append(run("C2 100x100x1 Efield.x=0.02, single lattice", 100, 100, 1, 1, 400, Efield=(0.02, 0, 0)))
 rows.append(run("C2 100x100x1, 64 replicas, colour-pass kernel (one launch per colour)", 100, 100, 1, 64, 100, Efield=(0.02, 0, 0), kernel=sn.SN_KERNEL_COLOUR))
 rows.append(run("C1 20x20x28 (make test lattice), 148 replicas", 20, 20, 28, 148, 40))
 rows.append(run("C1 20x20x28 (make test lattice), single lattice", 20, 20, 28, 1, 100))
+if QUICK:
+    raise SystemExit(0)
 rows.append(run("C3 64^3 CageStrain=1, T=0..500 K step 25 (21 replicas)", 64, 64, 64, 21, 40, temps=list(range(0, 501, 25))))
 rows.append(run("C4 128^3 solid solution (lengths 1.0/0.5/0.0 at 0.6/0.3/0.1)", 128, 128, 128, 1, 40, lengths=(1.0, 0.5, 0.0), prevalence=(0.6, 0.3, 0.1), Efield=(0.05, 0, 0)))
 rows.append(run("C4 128^3 solid solution, 8 field replicas", 128, 128, 128, 8, 20, lengths=(1.0, 0.5, 0.0), prevalence=(0.6, 0.3, 0.1), Efield=(0.05, 0, 0)))

@@ -21,27 +21,30 @@ namespace snr {
 constexpr int MAX_SMEM = 227 * 1024;
 __host__ __device__ constexpr int threads(int mode) { return mode == 1 ? 640 : 256; }   // 2-D: 625 sites per colour at 100x100
 
-// Shared-memory layout.  Threads of a colour pass own sites P = cutoff + 1 apart along the innermost
-// interacting axis (z, or y when Z == 1); stored naively their float4 would sit 64 B apart and every
-// LDS.128 of a warp would take 4x the wavefronts.  That axis is therefore de-interleaved by P: coordinate
-// v lives at (v % P) * ceil(n / P) + v / P, so the lanes of a pass read consecutive float4.  Per-axis
-// tables (built once per CTA) hold the element offset of every coordinate -cutoff .. n + cutoff - 1 with
-// the periodic wrap already applied; a neighbour address is three table entries added up.
+// Shared-memory layout: colour-major.  The threads of a colour pass own sites P = cutoff + 1 apart along every
+// interacting axis; stored in lattice order their float4 would sit 64 B (and whole rows) apart and every LDS.128
+// of a warp would take several times the wavefronts.  Every axis is therefore de-interleaved by its colour
+// period: site (x,y,z) lives at
+//     ((((x%Px) Py + y%Py) Pz + z%Pz) Qx + x/Px) Qy Qz + (y/Py) Qz + z/Pz,     Q = ceil(extent / P),
+// so all sites of one colour are contiguous in the order the threads walk them and a neighbour class is another
+// contiguous block: the lanes of a pass read consecutive float4 (bank-conflict free).  The index is a sum of
+// per-axis terms, kept in tables (built once per CTA) for every coordinate -cutoff .. n + cutoff - 1 with the
+// periodic wrap already applied; a neighbour address is three table entries added up.
 struct Layout {
-    int Py, Qy, Pz, Qz;     // de-interleave period and run length of y and z (period 1 = plain)
-    int sX, sY;             // element strides
-    int cells;              // float4 slots of the tile (>= X*Y*Z when an extent is not a multiple of P)
+    int Px, Qx, Py, Qy, Pz, Qz;
+    int A, B, C, D, E;      // element strides of x%Px, x/Px, y%Py, y/Py, z%Pz (z/Pz has stride 1)
+    int cells;              // float4 slots of the tile (>= X*Y*Z when an extent is not a multiple of its period)
     int g;                  // table margin = cutoff
     int tab_off;            // byte offset of the tables behind the tile
 };
-__host__ __device__ inline Layout layout(const SnGeom &G, int cutoff, int Pinner)
+__host__ __device__ inline Layout layout(const SnGeom &G, int cutoff, int Px, int Py, int Pz)
 {
     Layout L;
     L.g = cutoff;
-    if (G.Z > 1) { L.Pz = Pinner; L.Qz = (G.nz + Pinner - 1) / Pinner; L.Py = 1; L.Qy = G.Y; }
-    else { L.Py = Pinner; L.Qy = (G.Y + Pinner - 1) / Pinner; L.Pz = 1; L.Qz = 1; }
-    L.sY = L.Pz * L.Qz; L.sX = L.Py * L.Qy * L.sY;
-    L.cells = G.X * L.sX;
+    L.Px = Px; L.Py = Py; L.Pz = Pz;
+    L.Qx = (G.X + Px - 1) / Px; L.Qy = (G.Y + Py - 1) / Py; L.Qz = (G.nz + Pz - 1) / Pz;
+    L.D = L.Qz; L.B = L.Qy * L.Qz; L.E = L.Qx * L.B; L.C = Pz * L.E; L.A = Py * L.C;
+    L.cells = Px * L.A;
     L.tab_off = L.cells * 16;
     return L;
 }
@@ -58,9 +61,9 @@ sn_resident_kernel(const SnSweepArgs a, const snr::Layout L, const int nrep, con
     const int X = G.X, Y = G.Y, Z = G.nz, N = X * Y * Z, tid = threadIdx.x, nthr = blockDim.x, g = L.g;
     int *xtab = reinterpret_cast<int *>(sn_resident_smem + L.tab_off), *ytab = xtab + X + 2 * g, *ztab = ytab + Y + 2 * g;
     auto wrapn = [](int v, int n) { v %= n; return v < 0 ? v + n : v; };
-    for (int i = tid; i < X + 2 * g; i += nthr) xtab[i] = wrapn(i - g, X) * L.sX;
-    for (int i = tid; i < Y + 2 * g; i += nthr) { const int y = wrapn(i - g, Y); ytab[i] = ((y % L.Py) * L.Qy + y / L.Py) * L.sY; }
-    for (int i = tid; i < Z + 2 * g; i += nthr) { const int z = wrapn(i - g, Z); ztab[i] = (z % L.Pz) * L.Qz + z / L.Pz; }
+    for (int i = tid; i < X + 2 * g; i += nthr) { const int x = wrapn(i - g, X); xtab[i] = (x % L.Px) * L.A + (x / L.Px) * L.B; }
+    for (int i = tid; i < Y + 2 * g; i += nthr) { const int y = wrapn(i - g, Y); ytab[i] = (y % L.Py) * L.C + (y / L.Py) * L.D; }
+    for (int i = tid; i < Z + 2 * g; i += nthr) { const int z = wrapn(i - g, Z); ztab[i] = (z % L.Pz) * L.E + z / L.Pz; }
     __syncthreads();
 
     for (int rep = blockIdx.x; rep < nrep; rep += gridDim.x) {
@@ -77,6 +80,10 @@ sn_resident_kernel(const SnSweepArgs a, const snr::Layout L, const int nrep, con
         t.constrain = a.constrain; t.dim = a.dim;
         const uint4 key = a.rep_key[rep];
         int n_acc = 0, n_rej = 0, n_vac = 0;
+        // The regular colours (c < P) all have the same site counts, so a thread's first site of a pass has the same
+        // (i,j,k) in every one of them: decode once, not with four integer divisions per pass.
+        const int rnx = sn_axis_count(a.ax, 0), rny = sn_axis_count(a.ay, 0), rnz = sn_axis_count(a.az, 0);
+        const int rk = tid % rnz, rj = (tid / rnz) % rny, ri = tid / (rnz * rny);
 
         for (int s = 0; s < nsweeps; s++) {
             const unsigned long long sw = sweep0 + (unsigned long long)s;
@@ -84,8 +91,11 @@ sn_resident_kernel(const SnSweepArgs a, const snr::Layout L, const int nrep, con
             for (int cx = 0; cx < a.ax.ncol; cx++) for (int cy = 0; cy < a.ay.ncol; cy++) for (int cz = 0; cz < a.az.ncol; cz++) {
                 const int nx = sn_axis_count(a.ax, cx), ny = sn_axis_count(a.ay, cy), nz = sn_axis_count(a.az, cz);
                 const int total = nx * ny * nz;
+                const bool regular = nx == rnx && ny == rny && nz == rnz;
                 for (int idx = tid; idx < total; idx += nthr) {
-                    const int k = idx % nz, j = (idx / nz) % ny, i = idx / (nz * ny);
+                    int k, j, i;
+                    if (regular && idx == tid) { k = rk; j = rj; i = ri; }
+                    else { k = idx % nz; j = (idx / nz) % ny; i = idx / (nz * ny); }
                     const int x = sn_axis_coord(a.ax, cx, i), y = sn_axis_coord(a.ay, cy, j), z = sn_axis_coord(a.az, cz, k);
                     const int c = xtab[x + g] + ytab[y + g] + ztab[z + g];
                     const float4 old = tile[c];
@@ -146,7 +156,8 @@ bool sn_resident_supported(const sn_handle *h, std::string *why)
     const char *msg = nullptr;
     if (!G.periodic_z) msg = "Z-slab handle";
     else if ((long long)G.X * G.Y * G.Z * 16 > snr::MAX_SMEM ||
-             snr::smem_bytes(G, snr::layout(G, g, sn_axis_colour(G.Z > 1 ? G.Z : G.Y, g, false).P)) > snr::MAX_SMEM)
+             snr::smem_bytes(G, snr::layout(G, g, sn_axis_colour(G.X, g, false).P, sn_axis_colour(G.Y, g, false).P,
+                                            sn_axis_colour(G.Z, g, G.Z == 1).P)) > snr::MAX_SMEM)
         msg = "lattice does not fit in 227 KB of shared memory";
     else if (G.X < g || G.Y < g || (G.Z > 1 && G.Z < g)) msg = "an extent is smaller than DipoleCutOff";
     if (msg) { if (why) *why = msg; return false; }
@@ -156,7 +167,7 @@ bool sn_resident_supported(const sn_handle *h, std::string *why)
 template <int MODE, bool SPECIES>
 static int sn_resident_launch_t(sn_handle *h, const SnSweepArgs &a, long long nsweeps)
 {
-    const snr::Layout L = snr::layout(h->G, h->p.cutoff, h->G.Z > 1 ? a.az.P : a.ay.P);
+    const snr::Layout L = snr::layout(h->G, h->p.cutoff, a.ax.P, a.ay.P, a.az.P);
     const int smem = snr::smem_bytes(h->G, L);
     auto kern = sn_resident_kernel<MODE, SPECIES>;
     SN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
