@@ -36,14 +36,23 @@
 //     later ones corrected in registers for the earlier accepted moves (partner
 //     lane and the segment above via shuffles).  Every attempt is a full fresh dE
 //     over the cut-off sphere.
-//   * All 128 threads run one ~22 KB instruction stream (it has to stay inside the
-//     instruction cache: a first version with two 30 KB warp roles spent half its
-//     cycles waiting for instructions).  A thread gathers the fields of 2 sites;
-//     neighbours r and -r share the tensor T(r) = T(-r), so their moments are added
-//     first and the tensor applied once (582 instead of 798 FP ops per attempt).
-//   * Accepted moves are written to the shared tile and straight to global
-//     memory together with their ghost images (periodic faces, and the
-//     neighbouring GPU's ghost planes over NVLink for a Z-slab handle).
+//   * Two worker roles of 4 warps: role A gathers the columns that depend on the
+//     previous super-pass and runs the chain, role B gathers the rest one super-pass
+//     ahead and draws the proposals; a ninth warp schedules (work items,
+//     dependencies, TMA, version publishing).  A thread gathers the fields of 2
+//     sites; neighbours r and -r share the tensor T(r) = T(-r), so their moments are
+//     added first and the tensor applied once (582 instead of 798 FP ops per
+//     attempt).  The unrolled streams are shared by 4 warps each, which keeps
+//     instruction fetch off the critical path (profiles/experiments/ has what
+//     happens otherwise).
+//   * The tile's interior is written back once per tile, coalesced, under the next
+//     tile's TMA load; sites on a lattice / slab face also go to their ghost images
+//     (periodic faces, and the neighbouring GPU's ghost planes over NVLink for a
+//     Z-slab handle).
+//
+// SN_EXP_* macros switch single ingredients off (no loads, no FP, no chain, ...) for the
+// bottleneck experiments recorded in profiles/experiments/; they are never defined in a
+// product build.
 #pragma once
 
 #include <cuda.h>
