@@ -624,9 +624,13 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
     if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_rdf: not available on a Z-slab handle (radius-9 halo)");
     const int CUT = 9;                              // analysis.c:540
     std::vector<SnRdfOffset> off;
+    std::vector<long long> mult(SN_RDF_BINS, 0);    // lattice vectors per r^2 (both signs): the reference's count per site
     for (int dx = -CUT; dx <= CUT; dx++) for (int dy = -CUT; dy <= CUT; dy++) for (int dz = -CUT; dz <= CUT; dz++) {
         const int r2 = dx * dx + dy * dy + dz * dz;
         if (r2 >= SN_RDF_BINS) continue;            // r^2 == 81 is neither zeroed nor printed by the reference
+        mult[r2]++;
+        // one of {d, -d}: the kernel walks the upper half space and the origin, the sums of r^2 > 0 are doubled below
+        if (!(dx > 0 || (dx == 0 && dy > 0) || (dx == 0 && dy == 0 && dz >= 0))) continue;
         SnRdfOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.r2 = (short)r2;
         off.push_back(o);
     }
@@ -634,6 +638,7 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
     std::vector<int> first(SN_RDF_BINS + 1, 0);
     for (auto &o : off) first[o.r2 + 1]++;
     for (int b = 0; b < SN_RDF_BINS; b++) first[b + 1] += first[b];
+    const bool near = h->G.X >= CUT && h->G.Y >= CUT && h->G.nz >= CUT;
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     const int nblocks = (int)((n + 255) / 256);
     const size_t b_off = off.size() * sizeof(SnRdfOffset), b_first = first.size() * sizeof(int);
@@ -645,13 +650,15 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
     int *d_first = (int *)((char *)s + b_out + ((b_off + 15) / 16) * 16);
     SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));
     SN_CUDA_CHECK(cudaMemcpyAsync(d_first, first.data(), b_first, cudaMemcpyHostToDevice, h->stream));
-    sn_rdf_kernel<<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, d_first, SN_RDF_BINS, d_out);
+    if (near) sn_rdf_kernel<true><<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, d_first, SN_RDF_BINS, d_out);
+    else sn_rdf_kernel<false><<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, d_first, SN_RDF_BINS, d_out);
     SN_CUDA_CHECK(cudaGetLastError());
     std::vector<double> tot(2 * SN_RDF_BINS);
     if ((rc = sn_reduce_to_host(h, d_out, nblocks, 2 * SN_RDF_BINS, tot.data()))) return rc;
     for (int b = 0; b < SN_RDF_BINS; b++) {
-        fe_sum[b] = tot[2 * b]; afe_sum[b] = tot[2 * b + 1];
-        count[b] = (long long)(first[b + 1] - first[b]) * n;       // analysis.c:578, one count per (site, offset)
+        const double twice = b == 0 ? 1.0 : 2.0;
+        fe_sum[b] = twice * tot[2 * b]; afe_sum[b] = twice * tot[2 * b + 1];
+        count[b] = mult[b] * n;                                     // analysis.c:578, one count per (site, offset)
     }
     return SN_OK;
 }
@@ -676,7 +683,10 @@ static int sn_potential_device(sn_handle *h, int replica, size_t extra_bytes, do
     SnPotOffset *d_off = (SnPotOffset *)((char *)s + b_v);
     if (extra) *extra = (char *)s + b_v + b_off;
     SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(SnPotOffset), cudaMemcpyHostToDevice, h->stream));
-    sn_potential_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), *d_v);
+    if (h->G.X >= MAXR && h->G.Y >= MAXR && h->G.nz >= MAXR)
+        sn_potential_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), *d_v);
+    else
+        sn_potential_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), *d_v);
     SN_CUDA_CHECK(cudaGetLastError());
     return SN_OK;
 }
@@ -720,8 +730,13 @@ extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_off
     double *d_v = (double *)s;
     SnEfOffset *d_off = (SnEfOffset *)((char *)s + b_v);
     SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));
-    sn_efield_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(),
-                                                                          half_offset ? 0 : 1, d_v);
+    const int reach = cutoff + 1;                   // the half-offset variant walks dx down to -cutoff-1
+    if (h->G.X >= reach && h->G.Y >= reach && h->G.nz >= reach)
+        sn_efield_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(),
+                                                                                    half_offset ? 0 : 1, d_v);
+    else
+        sn_efield_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(),
+                                                                                     half_offset ? 0 : 1, d_v);
     SN_CUDA_CHECK(cudaGetLastError());
     SN_CUDA_CHECK(cudaMemcpyAsync(Emag, d_v, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));

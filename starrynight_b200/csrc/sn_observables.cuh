@@ -45,6 +45,15 @@ __device__ __forceinline__ void sn_block_sum(double (&v)[NV], double *smem /* NV
     __syncthreads();
 }
 
+// periodic wrap of v = coordinate + offset.  NEAR: |offset| <= n is guaranteed by the caller (every extent at least
+// the stencil radius), so one conditional add / subtract replaces the integer division.
+template <bool NEAR>
+__device__ __forceinline__ int sn_wrap(int v, int n)
+{
+    if constexpr (NEAR) { v += v < 0 ? n : 0; v -= v >= n ? n : 0; return v; }
+    else { v %= n; return v < 0 ? v + n : v; }
+}
+
 __device__ __forceinline__ void sn_site_of(const SnGeom &G, long long i, int &x, int &y, int &z)
 {
     z = (int)(i % G.nz); y = (int)((i / G.nz) % G.Y); x = (int)(i / ((long long)G.nz * G.Y));
@@ -125,11 +134,14 @@ __global__ void __launch_bounds__(128) sn_site_energy_f32_kernel(const float4 *_
 
 // ---- radial order parameter (analysis.c:528-598) ------------------------------
 // Offsets inside the radius-9 sphere are sorted by r^2 on the host; `first[b]`
-// is the first offset of bin b.  Each thread walks every offset for its site,
+// is the first offset of bin b.  Only one of every pair {d, -d} is walked: on a periodic lattice the
+// pairs (i, i+d) over all sites i are the pairs (j-d, j) over all j, and both correlations are symmetric
+// in their two dipoles, so the host doubles the sums of r^2 > 0 (half the 3071 pair terms per site).  Each thread walks every offset for its site,
 // keeps the running FE / AFE sums of the current bin in registers, and the block
 // reduces them once per bin -> out[block][bin][2].
 struct SnRdfOffset { short dx, dy, dz, r2; };
 
+template <bool NEAR>
 __global__ void __launch_bounds__(256) sn_rdf_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnRdfOffset *__restrict__ off,
                                                      const int *__restrict__ first, int nbins, double *__restrict__ out)
 {
@@ -145,10 +157,7 @@ __global__ void __launch_bounds__(256) sn_rdf_kernel(const float4 *__restrict__ 
         const int e = first[b + 1];
         for (int o = first[b]; o < e && live; o++) {
             const SnRdfOffset f = off[o];
-            int xx = (x + f.dx) % G.X, yy = (y + f.dy) % G.Y, zz = (z + f.dz) % G.nz;
-            if (xx < 0) xx += G.X;
-            if (yy < 0) yy += G.Y;
-            if (zz < 0) zz += G.nz;
+            const int xx = sn_wrap<NEAR>(x + f.dx, G.X), yy = sn_wrap<NEAR>(y + f.dy, G.Y), zz = sn_wrap<NEAR>(z + f.dz, G.nz);
             const float4 c = lat[sn_pidx(G, xx, yy, zz)];
             const double fe = (double)a.x * c.x + (double)a.y * c.y + (double)a.z * c.z;
             double afe = fe;
@@ -169,6 +178,7 @@ __global__ void __launch_bounds__(256) sn_rdf_kernel(const float4 *__restrict__ 
 // ---- electrostatic potential map (analysis.c:65-94) ---------------------------
 struct SnPotOffset { short dx, dy, dz, pad; double w; };   // w = 1/d^3
 
+template <bool NEAR>
 __global__ void __launch_bounds__(128) sn_potential_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnPotOffset *__restrict__ off,
                                                            int noff, double *__restrict__ V)
 {
@@ -179,10 +189,7 @@ __global__ void __launch_bounds__(128) sn_potential_kernel(const float4 *__restr
     double pot = 0.0;
     for (int o = 0; o < noff; o++) {
         const SnPotOffset f = off[o];
-        int xx = (x + f.dx) % G.X, yy = (y + f.dy) % G.Y, zz = (z + f.dz) % G.nz;
-        if (xx < 0) xx += G.X;
-        if (yy < 0) yy += G.Y;
-        if (zz < 0) zz += G.nz;
+        const int xx = sn_wrap<NEAR>(x + f.dx, G.X), yy = sn_wrap<NEAR>(y + f.dy, G.Y), zz = sn_wrap<NEAR>(z + f.dz, G.nz);
         const float4 c = lat[sn_pidx(G, xx, yy, zz)];
         pot += (double)c.w * ((double)c.x * f.dx + (double)c.y * f.dy + (double)c.z * f.dz) * f.w;
     }
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(128) sn_potential_kernel(const float4 *__restr
 // ---- dipole electric-field maps (analysis.c:310-376, 393-465) -------------------
 struct SnEfOffset { short dx, dy, dz, pad; double nx, ny, nz, w; };   // n = r/d, w = 1/d^3
 
+template <bool NEAR>
 __global__ void __launch_bounds__(128) sn_efield_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnEfOffset *__restrict__ off,
                                                         int noff, int self_term, double *__restrict__ Emag)
 {
@@ -202,10 +210,7 @@ __global__ void __launch_bounds__(128) sn_efield_kernel(const float4 *__restrict
     double ex = 0.0, ey = 0.0, ez = 0.0;
     for (int o = 0; o < noff; o++) {
         const SnEfOffset f = off[o];
-        int xx = (x + f.dx) % G.X, yy = (y + f.dy) % G.Y, zz = (z + f.dz) % G.nz;
-        if (xx < 0) xx += G.X;
-        if (yy < 0) yy += G.Y;
-        if (zz < 0) zz += G.nz;
+        const int xx = sn_wrap<NEAR>(x + f.dx, G.X), yy = sn_wrap<NEAR>(y + f.dy, G.Y), zz = sn_wrap<NEAR>(z + f.dz, G.nz);
         const float4 c = lat[sn_pidx(G, xx, yy, zz)];
         const double radial = f.nx * c.x + f.ny * c.y + f.nz * c.z;           // species length not applied (analysis.c:429-434)
         ex += (3.0 * f.nx * radial - c.x) * f.w;
