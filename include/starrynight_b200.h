@@ -51,7 +51,8 @@ typedef enum {
 
 /* arithmetic of the energy-audit entry points */
 typedef enum {
-    SN_PREC_F32 = 0,      /* the sweep kernel's own FP32 local-field arithmetic (1e-5 bar) */
+    SN_PREC_F32 = 0,      /* FP32 local-field arithmetic, the colour-pass / resident sweep kernels' own (1e-5 bar); the tiled
+                             kernel's register arithmetic is audited attempt by attempt with sn_mc_sweep_audit */
     SN_PREC_F64 = 1,      /* all-FP64, reference statement order (1e-12 bar vs the float->double reference build) */
     SN_PREC_REPLICA = 2   /* float terms + double accumulation exactly as montecarlo-core.c:99-121 (bit-equal to the native reference) */
 } sn_precision;
@@ -109,7 +110,10 @@ SN_API int sn_get_lattice(sn_handle *h, int replica, float *xyzlen);
  * CageStrain (main.c:149) between MC_moves calls */
 SN_API int sn_set_beta(sn_handle *h, int replica, double beta);
 SN_API int sn_set_efield(sn_handle *h, int replica, const float E[3]);
-SN_API int sn_set_cagestrain(sn_handle *h, double cagestrain);
+SN_API int sn_set_cagestrain(sn_handle *h, double cagestrain);           /* every replica */
+/* one replica: the reference's sweep mode is a T x CageStrain grid of independent runs (Makefile:52-54
+ * `superparallel`; argv[2] -> CageStrain, main.c:147-151), here one replica batch */
+SN_API int sn_set_replica_cagestrain(sn_handle *h, int replica, double cagestrain);
 
 /* replaces MC_moves(X*Y*Z*nsweeps) (montecarlo-core.c:143-149; main.c:222,248).
  * One sweep attempts one Metropolis update at every site of every replica, in
@@ -124,6 +128,19 @@ SN_API int sn_mc_sweeps(sn_handle *h, long long nsweeps);
 SN_API int sn_mc_sweeps_timed(sn_handle *h, long long nsweeps, double *ms, long long *launches);
 
 SN_API int sn_synchronize(sn_handle *h);
+
+/* Audit of MC_move (montecarlo-core.c:151-191) as the sweep kernel executes it: runs ONE sweep (it counts like
+ * sn_mc_sweeps(h, 1): same chain, same counters) and returns one record of SN_AUDIT_WORDS floats per attempt,
+ * records[replica][x][y][zlocal][8] =
+ *   { trial dipole x, y, z (config.c:203-263),  accept uniform u (:179),  dE the kernel used (:154),
+ *     decision: 1 accepted, 0 rejected, 2 vacant site skipped (:163),
+ *     group: ordinal of the set of mutually independent sites the attempt was made in -- attempts of a lower
+ *            group come before it in the chain, attempts of one group never read each other's sites,
+ *     0 }
+ * A host replay in group order on a copy of the lattice reproduces every dE with the reference's own
+ * site_energy (tests/test_gpu_audit.py).  Tiled handles run the tiled kernel itself (audit instantiation). */
+#define SN_AUDIT_WORDS 8
+SN_API int sn_mc_sweep_audit(sn_handle *h, float *records);
 
 /* replaces the globals ACCEPT / REJECT (config.c:26-27; montecarlo-core.c:187-190).
  * vacant = attempts that hit a length==0 site, which the reference neither
@@ -161,6 +178,12 @@ SN_API int sn_total_energy(sn_handle *h, int replica, int precision, double out[
 
 /* replaces polarisation() (analysis.c:48-62): P = (1/N) sum_i p_i, all three components */
 SN_API int sn_polarisation(sn_handle *h, int replica, double P[3]);
+/* 64-bit content hash of the handle's own sites (position-keyed, summed mod 2^64): the hashes of the Z-slabs of a
+ * decomposed lattice add up to the hash of the same lattice on one GPU iff every site holds the same bits.  The
+ * reference has nothing like it; bench.py and the multi-GPU tests use it to show N-GPU chain == 1-GPU chain. */
+SN_API int sn_state_hash(sn_handle *h, int replica, unsigned long long *hash);
+/* which sweep kernel sn_mc_sweeps runs on this handle (an sn_kernel value other than SN_KERNEL_AUTO) */
+SN_API int sn_kernel_in_use(sn_handle *h, int *kernel);
 /* replaces landau_order() (analysis.c:506-526): |sum_i p_i|^2 / N * N as written there */
 SN_API int sn_landau_order(sn_handle *h, int replica, double *landau);
 /* replaces radial_order_parameter() (analysis.c:528-598): accumulated sums and
@@ -176,6 +199,12 @@ SN_API int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_offset,
  * FD-Total-electron FD-Total-hole eMAX hMAX RMAX */
 #define SN_RECOMB_N 11
 SN_API int sn_recombination(sn_handle *h, int replica, double out[SN_RECOMB_N]);
+
+/* Test aid: Philox4x32-10 (Salmon et al., SC'11), the counter-based generator that replaces the reference's global
+ * MT19937 stream (mt19937ar-cok.c; montecarlo-core.c:159-161,179), evaluated for n inputs of 6 words
+ * (counter[4], key[2]) by the host build of the function and by the device.  out_* receive 4 words per input;
+ * out_device may be NULL (then no GPU is touched).  Checked against the Random123 known-answer vectors. */
+SN_API int sn_philox_kat(int n, const unsigned int *counter_key, unsigned int *out_host, unsigned int *out_device);
 
 /* measurement aid for bench.py: sustained FFMA throughput of `device` in TFLOP/s, the
  * denominator of the FP32 CUDA-core roofline (MEASURED_PEAKS.json carries no FP32 figure) */

@@ -27,11 +27,11 @@ SN_RDF_BINS = 81
 
 EXPORTS = [
     "sn_last_error", "sn_version", "sn_default_params", "sn_create", "sn_destroy", "sn_neighbour_table",
-    "sn_set_lattice", "sn_get_lattice", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_mc_sweeps",
+    "sn_set_lattice", "sn_get_lattice", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_set_replica_cagestrain", "sn_mc_sweeps", "sn_mc_sweep_audit",
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_set_counters",
     "sn_get_sweep_count", "sn_set_sweep_count", "sn_set_replica_seed", "sn_site_energy",
     "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_get_boundary",
-    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak",
+    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak", "sn_philox_kat", "sn_state_hash", "sn_kernel_in_use",
 ]
 
 
@@ -70,7 +70,9 @@ def load_library() -> C.CDLL:
     lib.sn_set_beta.argtypes = [H, C.c_int, C.c_double]
     lib.sn_set_efield.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     lib.sn_set_cagestrain.argtypes = [H, C.c_double]
+    lib.sn_set_replica_cagestrain.argtypes = [H, C.c_int, C.c_double]
     lib.sn_mc_sweeps.argtypes = [H, C.c_longlong]
+    lib.sn_mc_sweep_audit.argtypes = [H, C.c_void_p]
     lib.sn_mc_sweeps_timed.argtypes = [H, C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     lib.sn_synchronize.argtypes = [H]
     lib.sn_get_counters.argtypes = [H, C.c_int] + [C.POINTER(C.c_ulonglong)] * 3
@@ -93,6 +95,9 @@ def load_library() -> C.CDLL:
     lib.sn_ipc_attach.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     lib.sn_attach_peer.argtypes = [H, C.c_int, H]
     lib.sn_bench_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.sn_philox_kat.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sn_state_hash.argtypes = [H, C.c_int, C.POINTER(C.c_ulonglong)]
+    lib.sn_kernel_in_use.argtypes = [H, C.POINTER(C.c_int)]
     _lib = lib
     return lib
 
@@ -106,6 +111,15 @@ def default_params() -> sn_params:
 def _check(rc: int) -> None:
     if rc != 0:
         raise SnError(f"libstarrynight_b200 error {rc}: {load_library().sn_last_error().decode()}")
+
+
+def philox_kat(counter_key, device=False):
+    """sn_philox4x32_10 for rows of (counter[4], key[2]): returns (host words, device words or None)."""
+    ck = np.ascontiguousarray(counter_key, np.uint32).reshape(-1, 6)
+    host = np.zeros((len(ck), 4), np.uint32)
+    dev = np.zeros((len(ck), 4), np.uint32) if device else None
+    _check(load_library().sn_philox_kat(len(ck), ck.ctypes.data, host.ctypes.data, dev.ctypes.data if device else None))
+    return host, dev
 
 
 def beta_of_T(T: float) -> float:
@@ -196,8 +210,12 @@ class Simulation:
         e = (C.c_float * 3)(*[float(v) for v in E])
         _check(self.lib.sn_set_efield(self.h, replica, e))
 
-    def set_cagestrain(self, c):
-        _check(self.lib.sn_set_cagestrain(self.h, float(c)))
+    def set_cagestrain(self, c, replica=None):
+        """CageStrain of every replica, or of one (the reference's T x CageStrain grid, Makefile:52-54)."""
+        if replica is None:
+            _check(self.lib.sn_set_cagestrain(self.h, float(c)))
+        else:
+            _check(self.lib.sn_set_replica_cagestrain(self.h, int(replica), float(c)))
 
     # -- MC_moves (montecarlo-core.c:143): one sweep = X*Y*Z attempts
     def MC_sweeps(self, nsweeps=1):
@@ -210,6 +228,13 @@ class Simulation:
 
     def synchronize(self):
         _check(self.lib.sn_synchronize(self.h))
+
+    def MC_sweep_audit(self):
+        """One sweep with every attempt recorded: array [replica][x][y][z][8] =
+        (trial x, y, z, accept uniform, dE, decision 1/0/2=vacant, group ordinal, 0) -- sn_mc_sweep_audit."""
+        rec = np.zeros((self.nreplicas, self.X, self.Y, self.nz, 8), np.float32)
+        _check(self.lib.sn_mc_sweep_audit(self.h, rec.ctypes.data))
+        return rec
 
     def counters(self, replica=0):
         a, r, v = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
@@ -268,6 +293,17 @@ class Simulation:
         v = np.zeros(11, np.float64)
         _check(self.lib.sn_recombination(self.h, replica, v.ctypes.data))
         return v
+
+    def state_hash(self, replica=0):
+        """Position-keyed 64-bit hash of this handle's sites; slabs' hashes add (mod 2^64) to the full lattice's."""
+        v = C.c_ulonglong(0)
+        _check(self.lib.sn_state_hash(self.h, replica, C.byref(v)))
+        return v.value
+
+    def kernel_in_use(self):
+        v = C.c_int(0)
+        _check(self.lib.sn_kernel_in_use(self.h, C.byref(v)))
+        return v.value
 
     def set_replica_seed(self, seed, replica):
         _check(self.lib.sn_set_replica_seed(self.h, replica, int(seed)))

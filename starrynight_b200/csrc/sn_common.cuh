@@ -20,6 +20,7 @@
 
 #define SN_FLAGS_NEXT 32        // h->flags[32..33]: the tiled kernel's work counter (u64)
 #define SN_FLAGS_SPECIES 40     // h->flags[40]: result of the species scan in sn_set_lattice
+#define SN_FLAGS_ERR 44         // h->flags[44]: set by a device-side wait that ran out of time (a slab neighbour never arrived)
 #define SN_FLAGS_VER 64         // h->flags[64..]: tile versions, [rep][X/16][Y/16][nz/16 + 2]
 #define SN_MAX_NB 1024          // neighbour-table capacity in constant memory (cutoff <= 6)
 
@@ -33,6 +34,16 @@ struct SnGeom {
     long long rep_stride;       // sites per replica in the padded array
     int periodic_z;             // nz == Z: z ghosts are periodic images of this handle's own planes
 };
+
+// Device-side waits (slab handshake, tile dependencies) are bounded: a peer that never launches must not hang the
+// node.  When the bound passes the waiter raises SN_FLAGS_ERR and carries on; every sweep kernel of the handle then
+// drains without taking new work and the next host call that synchronises returns SN_ERR_CUDA.
+__device__ __forceinline__ unsigned long long sn_globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __host__ __device__ inline long long sn_pidx(const SnGeom &G, int x, int y, int z)
 {
@@ -102,6 +113,11 @@ __host__ __device__ inline Philox4 sn_philox4x32_10(uint32_t c0, uint32_t c1, ui
 
 // 24-bit uniform on [0,1)
 __host__ __device__ inline float sn_u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+// The accept test's uniform: all 32 bits, rounded to the nearest float -- the resolution of the reference's
+// genrand_real2 (montecarlo-core.c:179), so acceptance probabilities down to 2^-32 are taken at their rate (a
+// 24-bit uniform would cut them off at 6e-8: low temperatures).  Like genrand_real2 it can return 0 (always accept);
+// values that round up to 1.0f never accept a dE >= 0, as u -> 1 should.
+__host__ __device__ inline float sn_u01_32(uint32_t r) { return (float)r * (1.0f / 4294967296.0f); }
 
 #define SN_CUDA_CHECK(call)                                                                   \
     do {                                                                                      \
@@ -128,6 +144,7 @@ struct sn_handle {
     uint4 *rep_key = nullptr;           // device, per replica Philox key + counter tag
     unsigned long long sweep = 0;       // sweeps done so far (Philox counter word)
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // sn_mc_sweeps_timed
     int nnb = 0;
     std::vector<int> nb_dxyz;           // reference order (montecarlo-core.c:47-62)
     std::vector<float> nb_d;
@@ -135,6 +152,7 @@ struct sn_handle {
     int *d_nb_dxyz = nullptr;           // device copy of nb_dxyz for the exact-order audit kernels
     std::vector<float> h_beta;          // host mirrors of the per-replica couplings
     std::vector<float> h_efield;        // 3 per replica
+    std::vector<double> h_cage;         // CageStrain per replica, as given (device copy, rounded to float: efield[rep].w)
     bool species = true;                // false when every length is exactly 1 (skips the l_j multiplies)
     std::vector<char> rep_species;      // per replica: some length != 1
     bool use_tiled = false;
@@ -152,9 +170,11 @@ struct sn_handle {
     unsigned int phase_epoch = 0;
     bool peer_is_ipc[2] = {false, false};
     unsigned char ipc_key[2][64] = {};
+    unsigned long long spin_timeout_ns = 60ull * 1000000000ull;   // bound of device-side waits (env SN_SPIN_TIMEOUT_S)
     int num_sms = 148;
     int grid_limit = 0;                 // > 0: cap on the tiled kernel's persistent grid (slab neighbours sharing this device)
     void *tmap = nullptr;               // CUtensorMap storage for the tiled kernel (device-constant copy made at launch)
+    float *audit_dev = nullptr;         // set for the duration of sn_mc_sweep_audit: the sweep kernels record every attempt
     // scratch
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     void *staging = nullptr; size_t staging_bytes = 0;
@@ -173,3 +193,4 @@ int sn_energy_exact_launch(sn_handle *h, int replica, int precision, int n, cons
                            const float *d_newdip, double *d_out);
 int sn_energy_exact_map_launch(sn_handle *h, int replica, int precision, int which, double *d_out);
 int sn_scratch(sn_handle *h, size_t bytes, void **out);
+int sn_check_device_error(sn_handle *h);

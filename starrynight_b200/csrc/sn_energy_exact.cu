@@ -97,7 +97,7 @@ static SnExactArgs sn_exact_args(sn_handle *h, int replica)
     a.G = h->G;
     a.nb_dxyz = h->d_nb_dxyz;
     a.nnb = h->nnb;
-    a.cage = h->p.CageStrain; a.K = h->p.K;
+    a.cage = h->h_cage[replica]; a.K = h->p.K;
     a.Ex = h->h_efield[3 * replica]; a.Ey = h->h_efield[3 * replica + 1]; a.Ez = h->h_efield[3 * replica + 2];
     return a;
 }

@@ -6,6 +6,7 @@
 // TMA/shared-memory tile kernel (sn_sweep_tiled.cuh).  There is no CPU path.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -49,6 +50,17 @@ extern "C" int sn_default_params(sn_params *p)
     return SN_OK;
 }
 
+// Did a device-side wait of this handle run out of time?  (call after a stream synchronisation)
+int sn_check_device_error(sn_handle *h)
+{
+    unsigned int e = 0;
+    SN_CUDA_CHECK(cudaMemcpyAsync(&e, h->flags + SN_FLAGS_ERR, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (e) return sn_fail(SN_ERR_CUDA, "a device-side wait timed out after %.1f s: a Z-slab neighbour never ran its part of the sweep "
+                                       "(results of this handle are invalid)", h->spin_timeout_ns * 1e-9);
+    return SN_OK;
+}
+
 int sn_scratch(sn_handle *h, size_t bytes, void **out)
 {
     if (bytes > h->scratch_bytes) {
@@ -63,7 +75,7 @@ int sn_scratch(sn_handle *h, size_t bytes, void **out)
 
 // gen_neighbour(), montecarlo-core.c:38-72: order dx -> dy -> dz, 0 < d <= cutoff,
 // d = sqrt in float; ZCutOff = 0 when Z == 1.
-static void sn_build_neighbours(sn_handle *h)
+static int sn_build_neighbours(sn_handle *h)
 {
     const int c = h->p.cutoff, zc = h->p.Z == 1 ? 0 : c;
     h->nb_dxyz.clear(); h->nb_d.clear();
@@ -83,10 +95,11 @@ static void sn_build_neighbours(sn_handle *h)
         tab.push_back(e);
     }
     h->nnb = (int)h->nb_d.size();
-    cudaMalloc(&h->nb_table, sizeof(SnNbEntry) * std::max(1, h->nnb));
-    cudaMemcpy(h->nb_table, tab.data(), sizeof(SnNbEntry) * h->nnb, cudaMemcpyHostToDevice);
-    cudaMalloc(&h->d_nb_dxyz, sizeof(int) * 3 * std::max(1, h->nnb));
-    cudaMemcpy(h->d_nb_dxyz, h->nb_dxyz.data(), sizeof(int) * 3 * h->nnb, cudaMemcpyHostToDevice);
+    SN_CUDA_CHECK(cudaMalloc(&h->nb_table, sizeof(SnNbEntry) * std::max(1, h->nnb)));
+    SN_CUDA_CHECK(cudaMemcpy(h->nb_table, tab.data(), sizeof(SnNbEntry) * h->nnb, cudaMemcpyHostToDevice));
+    SN_CUDA_CHECK(cudaMalloc(&h->d_nb_dxyz, sizeof(int) * 3 * std::max(1, h->nnb)));
+    SN_CUDA_CHECK(cudaMemcpy(h->d_nb_dxyz, h->nb_dxyz.data(), sizeof(int) * 3 * h->nnb, cudaMemcpyHostToDevice));
+    return SN_OK;
 }
 
 // Slab handles of this process, by device.  Slabs of one lattice wait for each other's tile versions from inside
@@ -108,25 +121,21 @@ static void sn_slab_register(sn_handle *h, bool add)
     }
 }
 
+// (E_x, E_y, E_z, CageStrain) of one replica -> device (the sweep kernels read the four together)
+static int sn_push_couplings(sn_handle *h, int r)
+{
+    const float4 e4 = make_float4(h->h_efield[3 * r], h->h_efield[3 * r + 1], h->h_efield[3 * r + 2], (float)h->h_cage[r]);
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->efield + r, &e4, sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));      // e4 lives on this stack frame
+    return SN_OK;
+}
+
 static int sn_mode(const sn_handle *h) { return h->p.cutoff == 3 ? (h->p.Z == 1 ? 1 : 0) : 2; }
 
-extern "C" int sn_create(const sn_params *p, sn_handle **out)
+// Everything sn_create does once the handle exists; any failure returns through sn_create, which destroys the
+// partially built handle (stream, device buffers, registry entry) -- no early return leaks.
+static int sn_create_body(sn_handle *h, const sn_params *p)
 {
-    if (!p || !out) return sn_fail(SN_ERR_INVALID, "sn_create: null argument");
-    *out = nullptr;
-    if (p->X < 1 || p->Y < 1 || p->Z < 1) return sn_fail(SN_ERR_INVALID, "sn_create: lattice %dx%dx%d", p->X, p->Y, p->Z);
-    if (p->cutoff < 0 || p->cutoff > 6) return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: DipoleCutOff %d outside 0..6", p->cutoff);
-    if (p->nreplicas < 1) return sn_fail(SN_ERR_INVALID, "sn_create: nreplicas %d", p->nreplicas);
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return sn_fail(SN_ERR_CUDA, "sn_create: no CUDA device (this library has no CPU path)");
-    if (p->device < 0 || p->device >= ndev) return sn_fail(SN_ERR_INVALID, "sn_create: device %d of %d", p->device, ndev);
-    SN_CUDA_CHECK(cudaSetDevice(p->device));
-
-    sn_handle *h = new sn_handle();
-    h->p = *p;
-    if (h->p.nz <= 0) { h->p.nz = p->Z; h->p.z0 = 0; }
-    if (h->p.z0 < 0 || h->p.z0 + h->p.nz > p->Z) { delete h; return sn_fail(SN_ERR_INVALID, "sn_create: slab [%d,%d) outside Z=%d", h->p.z0, h->p.z0 + h->p.nz, p->Z); }
     SnGeom &G = h->G;
     G.X = p->X; G.Y = p->Y; G.Z = p->Z; G.z0 = h->p.z0; G.nz = h->p.nz;
     G.g = p->cutoff; G.gz = p->Z == 1 ? 0 : p->cutoff;
@@ -136,18 +145,17 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
     G.periodic_z = (G.nz == G.Z);
     if (!G.periodic_z) {
         const int P = p->cutoff + 1;
-        if (G.nz % P || G.z0 % P || G.Z % P || G.nz < p->cutoff) {
-            delete h;
+        if (G.nz % P || G.z0 % P || G.Z % P || G.nz < p->cutoff)
             return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: Z-slabs need z0, nz and Z to be multiples of cutoff+1 (z0=%d nz=%d Z=%d)", G.z0, G.nz, G.Z);
-        }
     }
     cudaDeviceProp prop;
     SN_CUDA_CHECK(cudaGetDeviceProperties(&prop, p->device));
     h->num_sms = prop.multiProcessorCount;
+    if (const char *t = getenv("SN_SPIN_TIMEOUT_S")) { const double v = atof(t); if (v > 0.0) h->spin_timeout_ns = (unsigned long long)(v * 1e9); }
     SN_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const size_t cells = (size_t)G.rep_stride * p->nreplicas;
     if (cudaMalloc(&h->lat, cells * sizeof(float4)) != cudaSuccess) {
-        cudaGetLastError(); cudaStreamDestroy(h->stream); delete h;
+        cudaGetLastError();
         return sn_fail(SN_ERR_NOMEM, "sn_create: cannot allocate %.1f MB for the lattice", cells * 16.0 / 1e6);
     }
     SN_CUDA_CHECK(cudaMemsetAsync(h->lat, 0, cells * sizeof(float4), h->stream));
@@ -173,38 +181,59 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
         SN_CUDA_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(unsigned int) * nflags, h->stream));
     }
     h->h_beta.assign(p->nreplicas, (float)p->beta);
+    h->h_cage.assign(p->nreplicas, p->CageStrain);
     h->rep_species.assign(p->nreplicas, 0);
     h->species = false;
     h->h_efield.resize(3 * (size_t)p->nreplicas);
-    std::vector<float4> e4(p->nreplicas);
-    for (int r = 0; r < p->nreplicas; r++) {
+    for (int r = 0; r < p->nreplicas; r++)
         for (int k = 0; k < 3; k++) h->h_efield[3 * r + k] = p->Efield[k];
-        e4[r] = make_float4(p->Efield[0], p->Efield[1], p->Efield[2], 0.f);
-    }
     SN_CUDA_CHECK(cudaMemcpyAsync(h->beta, h->h_beta.data(), sizeof(float) * p->nreplicas, cudaMemcpyHostToDevice, h->stream));
-    SN_CUDA_CHECK(cudaMemcpyAsync(h->efield, e4.data(), sizeof(float4) * p->nreplicas, cudaMemcpyHostToDevice, h->stream));
+    for (int r = 0; r < p->nreplicas; r++) { int rc = sn_push_couplings(h, r); if (rc) return rc; }
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    sn_build_neighbours(h);
+    { int rc = sn_build_neighbours(h); if (rc) return rc; }
     SN_CUDA_CHECK(cudaGetLastError());
 
     std::string why;
     const bool can_tile = sn_tiled_supported(h, &why);
-    if ((p->kernel == SN_KERNEL_TILED || p->kernel == SN_KERNEL_TILED_PHASED) && !can_tile) {
-        sn_destroy(h);
+    if ((p->kernel == SN_KERNEL_TILED || p->kernel == SN_KERNEL_TILED_PHASED) && !can_tile)
         return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: tiled kernel unavailable: %s", why.c_str());
-    }
     h->use_tiled = can_tile && p->kernel != SN_KERNEL_COLOUR && p->kernel != SN_KERNEL_RESIDENT;
     {
         std::string why_r;
         const bool can_reside = sn_resident_supported(h, &why_r);
-        if (p->kernel == SN_KERNEL_RESIDENT && !can_reside) {
-            sn_destroy(h);
+        if (p->kernel == SN_KERNEL_RESIDENT && !can_reside)
             return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: shared-memory-resident kernel unavailable: %s", why_r.c_str());
-        }
         h->use_resident = can_reside && !h->use_tiled && (p->kernel == SN_KERNEL_AUTO || p->kernel == SN_KERNEL_RESIDENT);
     }
-    if (h->use_tiled) { int rc = sn_tiled_prepare(h); if (rc) { sn_destroy(h); return rc; } }
+    if (h->use_tiled) { int rc = sn_tiled_prepare(h); if (rc) return rc; }
     if (!G.periodic_z) sn_slab_register(h, true);
+    return SN_OK;
+}
+
+extern "C" int sn_create(const sn_params *p, sn_handle **out)
+{
+    if (!p || !out) return sn_fail(SN_ERR_INVALID, "sn_create: null argument");
+    *out = nullptr;
+    if (p->X < 1 || p->Y < 1 || p->Z < 1) return sn_fail(SN_ERR_INVALID, "sn_create: lattice %dx%dx%d", p->X, p->Y, p->Z);
+    if (p->cutoff < 0 || p->cutoff > 6) return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: DipoleCutOff %d outside 0..6", p->cutoff);
+    if (p->nreplicas < 1) return sn_fail(SN_ERR_INVALID, "sn_create: nreplicas %d", p->nreplicas);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return sn_fail(SN_ERR_CUDA, "sn_create: no CUDA device (this library has no CPU path)");
+    if (p->device < 0 || p->device >= ndev) return sn_fail(SN_ERR_INVALID, "sn_create: device %d of %d", p->device, ndev);
+    SN_CUDA_CHECK(cudaSetDevice(p->device));
+
+    sn_handle *h = new sn_handle();
+    h->p = *p;
+    if (h->p.nz <= 0) { h->p.nz = p->Z; h->p.z0 = 0; }
+    h->G.periodic_z = 1;                              // until the geometry is known: sn_destroy must not touch the slab registry
+    if (h->p.z0 < 0 || h->p.z0 + h->p.nz > p->Z) {
+        const int z0 = h->p.z0, nz = h->p.nz;
+        delete h;
+        return sn_fail(SN_ERR_INVALID, "sn_create: slab [%d,%d) outside Z=%d", z0, z0 + nz, p->Z);
+    }
+    const int rc = sn_create_body(h, p);
+    if (rc) { sn_destroy(h); return rc; }             // sn_destroy leaves sn_last_error() untouched
     *out = h;
     return SN_OK;
 }
@@ -222,6 +251,7 @@ extern "C" int sn_destroy(sn_handle *h)
     }
     cudaFree(h->lat); cudaFree(h->beta); cudaFree(h->efield); cudaFree(h->counters); cudaFree(h->flags); cudaFree(h->rep_key);
     cudaFree(h->nb_table); cudaFree(h->d_nb_dxyz); cudaFree(h->d_scratch); cudaFree(h->staging);
+    for (int e = 0; e < 2; e++) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SN_OK;
@@ -313,7 +343,7 @@ extern "C" int sn_get_lattice(sn_handle *h, int replica, float *xyzlen)
     if (rc) return rc;
     if ((rc = sn_copy_block(h, replica, xyzlen, false))) return rc;
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    return SN_OK;
+    return sn_check_device_error(h);
 }
 
 extern "C" int sn_set_beta(sn_handle *h, int replica, double beta)
@@ -330,24 +360,33 @@ extern "C" int sn_set_efield(sn_handle *h, int replica, const float E[3])
     SN_CHECK_HANDLE(h, replica);
     if (!E) return sn_fail(SN_ERR_INVALID, "sn_set_efield: null");
     for (int k = 0; k < 3; k++) h->h_efield[3 * replica + k] = E[k];
-    const float4 e4 = make_float4(E[0], E[1], E[2], 0.f);
-    SN_CUDA_CHECK(cudaMemcpyAsync(h->efield + replica, &e4, sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    return SN_OK;
+    return sn_push_couplings(h, replica);
 }
 
 extern "C" int sn_set_cagestrain(sn_handle *h, double cagestrain)
 {
     SN_CHECK_HANDLE(h, 0);
     h->p.CageStrain = cagestrain;
+    for (int r = 0; r < h->p.nreplicas; r++) {
+        h->h_cage[r] = cagestrain;
+        int rc = sn_push_couplings(h, r);
+        if (rc) return rc;
+    }
     return SN_OK;
+}
+
+extern "C" int sn_set_replica_cagestrain(sn_handle *h, int replica, double cagestrain)
+{
+    SN_CHECK_HANDLE(h, replica);
+    h->h_cage[replica] = cagestrain;
+    return sn_push_couplings(h, replica);
 }
 
 extern "C" int sn_synchronize(sn_handle *h)
 {
     SN_CHECK_HANDLE(h, 0);
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    return SN_OK;
+    return sn_check_device_error(h);
 }
 
 // ---- sweeps -----------------------------------------------------------------
@@ -359,13 +398,14 @@ static SnSweepArgs sn_sweep_args(sn_handle *h)
     a.ay = sn_axis_colour(h->G.Y, h->p.cutoff, false);
     a.az = sn_axis_colour(h->G.nz, h->p.cutoff, h->G.Z == 1);
     a.beta = h->beta; a.efield = h->efield;
-    a.cage = (float)h->p.CageStrain; a.K = (float)h->p.K;
+    a.K = (float)h->p.K;
     a.constrain = h->p.ConstrainToX; a.dim = h->p.DIM;
     a.counters = h->counters;
     a.rep_key = h->rep_key;
     a.sweep_lo = (uint32_t)h->sweep; a.sweep_hi = (uint32_t)(h->sweep >> 32);
     a.nb = h->nb_table; a.nnb = h->nnb;
     a.peer_lo = h->peer_lat[0]; a.peer_hi = h->peer_lat[1];
+    a.audit = h->audit_dev; a.audit_group = 0;
     return a;
 }
 
@@ -385,6 +425,7 @@ int sn_sweep_colour_launch(sn_handle *h, long long nsweeps, long long *launches)
     for (long long s = 0; s < nsweeps; s++) {
         SnSweepArgs a = sn_sweep_args(h);
         for (int cx = 0; cx < a.ax.ncol; cx++) for (int cy = 0; cy < a.ay.ncol; cy++) for (int cz = 0; cz < a.az.ncol; cz++) {
+            a.audit_group = (cx * a.ay.ncol + cy) * a.az.ncol + cz;
             if (mode == 0) { if (h->species) sn_launch_colour<0, true>(a, h->p.nreplicas, cx, cy, cz, h->stream); else sn_launch_colour<0, false>(a, h->p.nreplicas, cx, cy, cz, h->stream); }
             else if (mode == 1) { if (h->species) sn_launch_colour<1, true>(a, h->p.nreplicas, cx, cy, cz, h->stream); else sn_launch_colour<1, false>(a, h->p.nreplicas, cx, cy, cz, h->stream); }
             else sn_launch_colour<2, true>(a, h->p.nreplicas, cx, cy, cz, h->stream);
@@ -415,20 +456,46 @@ extern "C" int sn_mc_sweeps(sn_handle *h, long long nsweeps)
 extern "C" int sn_mc_sweeps_timed(sn_handle *h, long long nsweeps, double *ms, long long *launches)
 {
     SN_CHECK_HANDLE(h, 0);
-    cudaEvent_t e0, e1;
-    SN_CUDA_CHECK(cudaEventCreate(&e0));
-    SN_CUDA_CHECK(cudaEventCreate(&e1));
+    if (!h->ev[0]) { SN_CUDA_CHECK(cudaEventCreate(&h->ev[0])); }     // owned by the handle, released in sn_destroy
+    if (!h->ev[1]) { SN_CUDA_CHECK(cudaEventCreate(&h->ev[1])); }
     long long n = 0;
-    SN_CUDA_CHECK(cudaEventRecord(e0, h->stream));
+    SN_CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
     int rc = sn_sweeps_impl(h, nsweeps, &n);
-    SN_CUDA_CHECK(cudaEventRecord(e1, h->stream));
-    SN_CUDA_CHECK(cudaEventSynchronize(e1));
+    SN_CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+    SN_CUDA_CHECK(cudaEventSynchronize(h->ev[1]));
     float t = 0.f;
-    SN_CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    SN_CUDA_CHECK(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
     if (ms) *ms = t;
     if (launches) *launches = n;
     return rc;
+}
+
+// One sweep with every attempt recorded (see the header).  Tiled handles run the AUDIT instantiation of the
+// tiled kernel -- same arithmetic, same order; every other handle runs the colour passes (the resident kernel's
+// chain is bit-identical to them).
+extern "C" int sn_mc_sweep_audit(sn_handle *h, float *records)
+{
+    SN_CHECK_HANDLE(h, 0);
+    if (!records) return sn_fail(SN_ERR_INVALID, "sn_mc_sweep_audit: null buffer");
+    if (!h->G.periodic_z && (!h->peer_lat[0] || !h->peer_lat[1]))
+        return sn_fail(SN_ERR_INVALID, "sn_mc_sweep_audit: Z-slab handle has no neighbours attached");
+    const size_t bytes = sizeof(float) * SN_AUDIT_WORDS * (size_t)h->p.nreplicas * h->G.X * h->G.Y * h->G.nz;
+    float *dev = nullptr;
+    if (cudaMalloc(&dev, bytes) != cudaSuccess) { cudaGetLastError(); return sn_fail(SN_ERR_NOMEM, "sn_mc_sweep_audit: cannot allocate %.1f MB", bytes / 1e6); }
+    int rc = SN_OK;
+    cudaError_t e = cudaMemsetAsync(dev, 0, bytes, h->stream);
+    if (e == cudaSuccess) {
+        h->audit_dev = dev;
+        rc = h->use_tiled ? sn_sweep_tiled_launch(h, 1, nullptr) : sn_sweep_colour_launch(h, 1, nullptr);
+        h->audit_dev = nullptr;
+        if (!rc) e = cudaMemcpyAsync(records, dev, bytes, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    else cudaStreamSynchronize(h->stream);
+    cudaFree(dev);
+    if (rc) return rc;
+    if (e != cudaSuccess) return sn_fail(SN_ERR_CUDA, "sn_mc_sweep_audit: %s", cudaGetErrorString(e));
+    return SN_OK;
 }
 
 extern "C" int sn_get_counters(sn_handle *h, int replica, unsigned long long *accept, unsigned long long *reject,
@@ -438,6 +505,7 @@ extern "C" int sn_get_counters(sn_handle *h, int replica, unsigned long long *ac
     unsigned long long c[3];
     SN_CUDA_CHECK(cudaMemcpyAsync(c, h->counters + 3 * replica, sizeof c, cudaMemcpyDeviceToHost, h->stream));
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    { int rc = sn_check_device_error(h); if (rc) return rc; }
     if (accept) *accept = c[0];
     if (reject) *reject = c[1];
     if (vacant) *vacant = c[2];
@@ -502,7 +570,7 @@ extern "C" int sn_set_counters(sn_handle *h, int replica, unsigned long long acc
 static SnTerms sn_terms(const sn_handle *h, int replica)
 {
     SnTerms t;
-    t.cage = (float)h->p.CageStrain; t.K = (float)h->p.K; t.beta = h->h_beta[replica];
+    t.cage = (float)h->h_cage[replica]; t.K = (float)h->p.K; t.beta = h->h_beta[replica];
     t.E = make_float3(h->h_efield[3 * replica], h->h_efield[3 * replica + 1], h->h_efield[3 * replica + 2]);
     t.constrain = h->p.ConstrainToX; t.dim = h->p.DIM;
     return t;
@@ -602,6 +670,31 @@ extern "C" int sn_polarisation(sn_handle *h, int replica, double P[3])
     if (rc) return rc;
     const double n = (double)h->G.X * h->G.Y * h->G.nz;    // analysis.c:60
     for (int k = 0; k < 3; k++) P[k] /= n;
+    return SN_OK;
+}
+
+extern "C" int sn_state_hash(sn_handle *h, int replica, unsigned long long *hash)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!hash) return sn_fail(SN_ERR_INVALID, "sn_state_hash: null");
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
+    void *s; int rc = sn_scratch(h, 64, &s);
+    if (rc || (rc = sn_sync_canonical(h))) return rc;
+    SN_CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(unsigned long long), h->stream));
+    sn_state_hash_kernel<<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, (unsigned long long *)s);
+    SN_CUDA_CHECK(cudaGetLastError());
+    SN_CUDA_CHECK(cudaMemcpyAsync(hash, s, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return sn_check_device_error(h);
+}
+
+extern "C" int sn_kernel_in_use(sn_handle *h, int *kernel)
+{
+    SN_CHECK_HANDLE(h, 0);
+    if (!kernel) return sn_fail(SN_ERR_INVALID, "sn_kernel_in_use: null");
+    *kernel = h->use_resident ? SN_KERNEL_RESIDENT : h->use_tiled ? (h->p.kernel == SN_KERNEL_TILED_PHASED ? SN_KERNEL_TILED_PHASED : SN_KERNEL_TILED)
+                                                                  : SN_KERNEL_COLOUR;
     return SN_OK;
 }
 
@@ -770,6 +863,39 @@ extern "C" int sn_recombination(sn_handle *h, int replica, double out[SN_RECOMB_
     out[5] = N * sum[4] / (ZFDe * ZFDh);                                      // R_FD = N * sum e_i h_i (:169)
     out[6] = sum[2] / ZFDe; out[7] = sum[3] / ZFDh;                            // FD totals (:163-164)
     out[8] = mx[0] / ZFDe; out[9] = mx[1] / ZFDh; out[10] = mx[2] / (ZFDe * ZFDh);   // maxima over z = 0 (:157-159)
+    return SN_OK;
+}
+
+// ---- Philox known-answer check ---------------------------------------------------
+__global__ void sn_philox_kat_kernel(int n, const uint32_t *__restrict__ in, uint32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Philox4 r = sn_philox4x32_10(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5]);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+// sn_philox4x32_10 -- the generator every sweep kernel draws from -- evaluated for n (counter[4], key[2]) inputs
+// by the host compilation of the function (out_host) and by the device (out_device; pass NULL to skip: no GPU needed).
+extern "C" int sn_philox_kat(int n, const unsigned int *counter_key, unsigned int *out_host, unsigned int *out_device)
+{
+    if (n < 0 || (n > 0 && !counter_key)) return sn_fail(SN_ERR_INVALID, "sn_philox_kat: bad arguments");
+    if (out_host)
+        for (int i = 0; i < n; i++) {
+            const unsigned int *c = counter_key + 6 * i;
+            const Philox4 r = sn_philox4x32_10(c[0], c[1], c[2], c[3], c[4], c[5]);
+            out_host[4 * i] = r.x; out_host[4 * i + 1] = r.y; out_host[4 * i + 2] = r.z; out_host[4 * i + 3] = r.w;
+        }
+    if (out_device && n > 0) {
+        uint32_t *d_in = nullptr, *d_out = nullptr;
+        cudaError_t e = cudaMalloc(&d_in, sizeof(uint32_t) * 6 * n);
+        if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(uint32_t) * 4 * n);
+        if (e == cudaSuccess) e = cudaMemcpy(d_in, counter_key, sizeof(uint32_t) * 6 * n, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { sn_philox_kat_kernel<<<(n + 127) / 128, 128>>>(n, d_in, d_out); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaMemcpy(out_device, d_out, sizeof(uint32_t) * 4 * n, cudaMemcpyDeviceToHost);
+        cudaFree(d_in); cudaFree(d_out);
+        if (e != cudaSuccess) return sn_fail(SN_ERR_CUDA, "sn_philox_kat: %s", cudaGetErrorString(e));
+    }
     return SN_OK;
 }
 

@@ -74,6 +74,35 @@ __global__ void __launch_bounds__(256) sn_sum_dipoles_kernel(const float4 *__res
     if (threadIdx.x == 0) { out[3 * blockIdx.x] = v[0]; out[3 * blockIdx.x + 1] = v[1]; out[3 * blockIdx.x + 2] = v[2]; }
 }
 
+// 64-bit content hash of the handle's own sites: sum over sites (mod 2^64) of a splitmix64 of the GLOBAL site index
+// and the four float bit patterns.  A sum, so slabs add up: the hash of a Z-slab decomposed lattice is the wrapped sum
+// of the slabs' hashes and equals the single-GPU hash iff every site holds the same bits.
+__device__ __forceinline__ unsigned long long sn_mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) sn_state_hash_kernel(const float4 *__restrict__ lat, const SnGeom G, unsigned long long *__restrict__ out)
+{
+    const long long n = (long long)G.X * G.Y * G.nz;
+    unsigned long long acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int x, y, z; sn_site_of(G, i, x, y, z);
+        const float4 p = lat[sn_pidx(G, x, y, z)];
+        const unsigned long long gsite = ((unsigned long long)x * G.Y + y) * G.Z + (G.z0 + z);
+        unsigned long long hsh = sn_mix64(gsite);
+        hsh = sn_mix64(hsh ^ (((unsigned long long)__float_as_uint(p.x) << 32) | __float_as_uint(p.y)));
+        hsh = sn_mix64(hsh ^ (((unsigned long long)__float_as_uint(p.z) << 32) | __float_as_uint(p.w)));
+        acc += hsh;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // generic deterministic reduction of n doubles into gridDim.x partials
 __global__ void __launch_bounds__(256) sn_sum_doubles_kernel(const double *__restrict__ in, long long n, double *__restrict__ out)
 {

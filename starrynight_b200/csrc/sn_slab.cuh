@@ -19,13 +19,17 @@ __global__ void sn_phase_signal_kernel(unsigned int *to_lower, unsigned int *to_
     if (to_upper) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(to_upper), "r"(epoch) : "memory"); }
 }
 
-__global__ void sn_phase_wait_kernel(const unsigned int *flags, unsigned int epoch)
+__global__ void sn_phase_wait_kernel(unsigned int *flags, unsigned int epoch, unsigned long long timeout_ns)
 {
+    const unsigned long long t0 = sn_globaltimer_ns();
     for (int s = 0; s < 2; s++) {
         unsigned int v;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + s) : "memory");
-        } while ((int)(v - epoch) < 0);
+            if ((int)(v - epoch) >= 0) break;
+            if (sn_globaltimer_ns() - t0 > timeout_ns) { atomicExch(flags + SN_FLAGS_ERR, 1u); return; }   // the neighbour never arrived
+            __nanosleep(200);
+        }
     }
 }
 
@@ -36,7 +40,7 @@ static int sn_slab_phase_sync(sn_handle *h, long long *launches)
     // my lower neighbour reads my signal in its slot 1 ("from above"), my upper neighbour in its slot 0
     sn_phase_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer_flags[0] ? h->peer_flags[0] + 1 : nullptr,
                                                    h->peer_flags[1] ? h->peer_flags[1] + 0 : nullptr, h->phase_epoch);
-    sn_phase_wait_kernel<<<1, 1, 0, h->stream>>>(h->flags, h->phase_epoch);
+    sn_phase_wait_kernel<<<1, 1, 0, h->stream>>>(h->flags, h->phase_epoch, h->spin_timeout_ns);
     SN_CUDA_CHECK(cudaGetLastError());
     if (launches) *launches += 2;
     return SN_OK;

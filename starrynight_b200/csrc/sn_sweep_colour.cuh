@@ -17,8 +17,8 @@ struct SnSweepArgs {
     SnGeom G;
     SnAxisColour ax, ay, az;
     const float *beta;              // per replica
-    const float4 *efield;           // per replica
-    float cage, K;
+    const float4 *efield;           // per replica: (E_x, E_y, E_z, CageStrain)
+    float K;
     int constrain, dim;
     unsigned long long *counters;   // per replica {accept, reject, vacant}
     const uint4 *rep_key;           // per replica: Philox key (x, y) and the tag xor-ed into counter word 1 (z)
@@ -26,7 +26,18 @@ struct SnSweepArgs {
     const SnNbEntry *nb;
     int nnb;
     float4 *peer_lo, *peer_hi;      // Z-slab neighbours' padded lattices (replica 0 base) or null
+    float *audit;                   // sn_mc_sweep_audit: one SN_AUDIT_WORDS record per attempt, [rep][x][y][z], or null
+    int audit_group;                // ordinal of this launch's group of mutually independent sites
 };
+
+// One audit record (include/starrynight_b200.h, sn_mc_sweep_audit): what the kernel proposed, drew, computed and decided.
+__device__ __forceinline__ void sn_audit_write(float *__restrict__ audit, const SnGeom &G, int rep, int x, int y, int z,
+                                               const float3 np, float u, float dE, bool accepted, bool vacant, int group)
+{
+    float4 *r = reinterpret_cast<float4 *>(audit + ((((long long)rep * G.X + x) * G.Y + y) * G.nz + z) * SN_AUDIT_WORDS);
+    r[0] = make_float4(np.x, np.y, np.z, u);
+    r[1] = make_float4(dE, vacant ? 2.0f : (accepted ? 1.0f : 0.0f), (float)group, 0.0f);
+}
 
 // Ghost images of a boundary site: periodic images in x, y (and z when the handle
 // owns the whole Z), and the neighbouring slabs' ghost planes.  Rare (surface
@@ -120,8 +131,10 @@ __global__ void __launch_bounds__(128) sn_colour_pass_kernel(const SnSweepArgs a
         float4 *lat = a.lat + (long long)rep * a.G.rep_stride;
         const float4 *site = lat + sn_pidx(a.G, x, y, z);
         const float4 old = *site;
-        if (old.w == 0.0f) vacant = true;                       // montecarlo-core.c:163
-        else {
+        if (old.w == 0.0f) {                                    // montecarlo-core.c:163
+            vacant = true;
+            if (a.audit) sn_audit_write(a.audit, a.G, rep, x, y, z, make_float3(0.f, 0.f, 0.f), 0.f, 0.f, false, true, a.audit_group);
+        } else {
             attempted = true;
             float3 F = make_float3(0.f, 0.f, 0.f), Gc = make_float3(0.f, 0.f, 0.f);
             const long long sx = a.G.sx, sy = a.G.sy;
@@ -130,8 +143,8 @@ __global__ void __launch_bounds__(128) sn_colour_pass_kernel(const SnSweepArgs a
             else if constexpr (MODE == 1) sn_local_field_cut3<true, SPECIES>(load, F, Gc);
             else sn_local_field_table(a.nb, a.nnb, load, F, Gc);
             SnTerms t;
-            t.cage = a.cage; t.K = a.K; t.beta = a.beta[rep];
             const float4 E = a.efield[rep];
+            t.cage = E.w; t.K = a.K; t.beta = a.beta[rep];
             t.E = make_float3(E.x, E.y, E.z);
             t.constrain = a.constrain; t.dim = a.dim;
             const unsigned long long gsite = ((unsigned long long)x * a.G.Y + y) * a.G.Z + (a.G.z0 + z);
@@ -139,7 +152,9 @@ __global__ void __launch_bounds__(128) sn_colour_pass_kernel(const SnSweepArgs a
             const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ key.z, a.sweep_lo, a.sweep_hi, key.x, key.y);
             const float3 np = sn_propose(t, sn_u01(r.x), sn_u01(r.y));
             const float dE = sn_delta_e(old, np, F, Gc, t);
-            accepted = sn_accept(dE, t.beta, sn_u01(r.z));
+            const float ua = sn_u01_32(r.z);
+            accepted = sn_accept(dE, t.beta, ua);
+            if (a.audit) sn_audit_write(a.audit, a.G, rep, x, y, z, np, ua, dE, accepted, false, a.audit_group);
             if (accepted) {
                 float4 *plo = a.peer_lo ? a.peer_lo + (long long)rep * a.G.rep_stride : nullptr;
                 float4 *phi = a.peer_hi ? a.peer_hi + (long long)rep * a.G.rep_stride : nullptr;

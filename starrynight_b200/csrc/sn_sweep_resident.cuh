@@ -75,8 +75,8 @@ sn_resident_kernel(const SnSweepArgs a, const snr::Layout L, const int nrep, con
         __syncthreads();
 
         SnTerms t;
-        t.cage = a.cage; t.K = a.K; t.beta = a.beta[rep];
-        { const float4 E = a.efield[rep]; t.E = make_float3(E.x, E.y, E.z); }
+        t.K = a.K; t.beta = a.beta[rep];
+        { const float4 E = a.efield[rep]; t.E = make_float3(E.x, E.y, E.z); t.cage = E.w; }
         t.constrain = a.constrain; t.dim = a.dim;
         const uint4 key = a.rep_key[rep];
         int n_acc = 0, n_rej = 0, n_vac = 0;
@@ -120,7 +120,7 @@ sn_resident_kernel(const SnSweepArgs a, const snr::Layout L, const int nrep, con
                     const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ key.z, sweep_lo, sweep_hi, key.x, key.y);
                     const float3 np = sn_propose(t, sn_u01(r.x), sn_u01(r.y));
                     const float dE = sn_delta_e(old, np, F, Gc, t);
-                    const bool accepted = sn_accept(dE, t.beta, sn_u01(r.z));
+                    const bool accepted = sn_accept(dE, t.beta, sn_u01_32(r.z));
                     if (accepted) tile[c] = make_float4(np.x, np.y, np.z, old.w);
                     n_acc += accepted; n_rej += !accepted;
                 }

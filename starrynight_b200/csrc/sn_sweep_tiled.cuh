@@ -285,6 +285,9 @@ struct SnTileFlow {
     unsigned int *ver;                  // [rep][2hx][2hy][2hz + 2] tile versions; z index shifted by one ghost layer
     unsigned int *peer_ver_lo, *peer_ver_hi;   // where my bottom / top tile layer is a ghost layer: the slab neighbours' arrays, or `ver` itself
     int sys_scope;                      // ghost versions and planes are written by other GPUs
+    float *audit;                       // AUDIT instantiation: one record per attempt (sn_audit_write), else unused
+    unsigned int *err;                  // SN_FLAGS_ERR of this handle: raised when a dependency wait runs out of time
+    unsigned long long timeout_ns;      // bound of one dependency wait
 };
 
 struct __align__(16) SnTileItem {
@@ -363,7 +366,9 @@ __device__ __forceinline__ void sn_tile_publish(const SnTileFlow &f, const SnTil
     }
 }
 
-template <bool SPECIES>
+// AUDIT: every attempt also leaves a record (proposal, accept uniform, the dE the chain used, decision, group
+// ordinal) for sn_mc_sweep_audit; the arithmetic and the order are those of the product instantiation.
+template <bool SPECIES, bool AUDIT>
 __global__ void __launch_bounds__(snt::THREADS, 1)
 sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, const SnTileFlow fl)
 {
@@ -432,15 +437,29 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     auto take = [&]() -> SnTileItem {
         unsigned long long n = lane == 0 ? fl.n_begin + atomicAdd(fl.next, 1ULL) : 0ULL;
         n = __shfl_sync(0xffffffffu, n, 0);
+        const unsigned int failed = *reinterpret_cast<volatile unsigned int *>(fl.err);     // a wait timed out somewhere: drain
         SnTileItem it;
         it.valid = 0; it.ready = 0;
-        if (n < fl.n_end) it = sn_tile_item(fl, n);
+        if (n < fl.n_end && !failed) it = sn_tile_item(fl, n);
         return it;
+    };
+    // Blocking wait for an item's dependencies, bounded: if a neighbour (another CTA, or a slab neighbour's kernel on
+    // another GPU that was never launched) does not get there in time, raise the handle's error flag and go on -- the
+    // tile's result is meaningless, every control warp stops taking items, and the host call that synchronises fails.
+    auto wait_deps = [&](const SnTileItem &it) {
+        const unsigned long long t0 = sn_globaltimer_ns();
+        while (!sn_tile_deps_ready(fl, it, lane)) {
+            __nanosleep(100);
+            if (sn_globaltimer_ns() - t0 > fl.timeout_ns || *reinterpret_cast<volatile unsigned int *>(fl.err)) {
+                if (lane == 0) atomicExch(fl.err, 1u);
+                break;
+            }
+        }
     };
     if (ctrl) {
         SnTileItem cur = take();
         if (cur.valid) {
-            while (!sn_tile_deps_ready(fl, cur, lane)) __nanosleep(100);
+            wait_deps(cur);
             deps_met();
             if (lane == 0) issue_tile_load(cur);
         }
@@ -463,7 +482,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             __syncwarp();
             if (lane == 0) sn_tile_publish(fl, cur);
             if (nxt.valid && !ready) {
-                while (!sn_tile_deps_ready(fl, nxt, lane)) __nanosleep(100);
+                wait_deps(nxt);
                 deps_met();
                 if (lane == 0) issue_tile_load(nxt);
             }
@@ -482,8 +501,8 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         const uint32_t sweep_lo = (uint32_t)item.sweep, sweep_hi = (uint32_t)(item.sweep >> 32);
 
         SnTerms tm;
-        tm.cage = a.cage; tm.K = a.K; tm.beta = a.beta[rep];
-        { const float4 E = a.efield[rep]; tm.E = make_float3(E.x, E.y, E.z); }
+        tm.K = a.K; tm.beta = a.beta[rep];
+        { const float4 E = a.efield[rep]; tm.E = make_float3(E.x, E.y, E.z); tm.cage = E.w; }
         tm.constrain = a.constrain; tm.dim = a.dim;
         const uint4 rkey = a.rep_key[rep];
         // a.lat / a.peer_* are the z-de-interleaved copies here (layout sn_pidx2)
@@ -494,7 +513,9 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         const bool face_tile = x0 == 0 || x0 + snt::T == G.X || y0 == 0 || y0 + snt::T == G.Y || z0 == 0 || z0 + snt::T == G.nz;
 
         // Trial orientations for the thread's 2 sites in super-pass sp from ONE Philox4x32-10 call keyed by
-        // (global site of the first one, replica, sweep): per site 64 random bits = 24 (accept) + 20 + 20.
+        // (global site of the first one, replica, sweep): per site 64 random bits = 32 (accept) + 20 + 20, the low 8
+        // bits of the accept word doubling as the last bits of the azimuth (they only reach the accept uniform
+        // when it is below 2^-8, as resolution beyond 2^-24).
         auto draw = [&](int sp) {
             const int gx = x0 + (sp >> 2) + 4 * i, gy = y0 + (sp & 3) + 4 * j, gz = z0 + 4 * k + 2 * h;
             const unsigned long long gsite = ((unsigned long long)gx * G.Y + gy) * G.Z + (G.z0 + gz);
@@ -506,7 +527,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                 const float u = (float)(wb[s] >> 12) * (1.0f / 1048576.0f);
                 const float v = (float)(((wb[s] & 0xfffu) << 8) | (wa[s] & 0xffu)) * (1.0f / 1048576.0f);
                 const float3 np = sn_propose(tm, u, v);
-                dst[s * snt::SITE_THREADS] = make_float4(np.x, np.y, np.z, sn_u01(wa[s]));
+                dst[s * snt::SITE_THREADS] = make_float4(np.x, np.y, np.z, sn_u01_32(wa[s]));
             }
         };
         if (role == 1) draw(0);                          // overlaps the TMA flight
@@ -612,6 +633,9 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                     if (acc) *const_cast<float4 *>(pe[3 + s]) = make_float4(np[s].x, np[s].y, np[s].z, old[s].w);
 #endif
                     n_acc += acc; n_rej += (mine & !acc & !vac[s]); n_vac += (mine & vac[s]);
+                    if constexpr (AUDIT) {
+                        if (mine) sn_audit_write(fl.audit, G, rep, gx, gy, gz + s, np[s], ua[s], dE, acc, vac[s], (item.p * 16 + sp) * 4 + t4);
+                    }
                     if (t4 < 3) {
                         const int srcS = (lane & 23) | ((t4 >> 1) << 3);            // owner of step t4 in this segment
                         const int srcU = (((lane & 23) + 1) & 31) | ((t4 >> 1) << 3);   // ... in the segment above (k + 1)
@@ -732,8 +756,10 @@ int sn_tiled_prepare(sn_handle *h)
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete tm; return sn_fail(SN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); }
     h->tmap = tm;
-    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
-    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
+    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
+    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
+    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
+    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
     return SN_OK;
 }
 
@@ -790,14 +816,20 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
     f.peer_ver_lo = G.periodic_z ? f.ver : h->peer_flags[0] + SN_FLAGS_VER;
     f.peer_ver_hi = G.periodic_z ? f.ver : h->peer_flags[1] + SN_FLAGS_VER;
     f.sys_scope = !G.periodic_z;
+    f.audit = h->audit_dev;
+    f.err = h->flags + SN_FLAGS_ERR;
+    f.timeout_ns = h->spin_timeout_ns;
     const unsigned long long P = (unsigned long long)f.hx * f.hy * f.hz * f.nrep;      // items per phase
     auto launch = [&](unsigned long long n0, unsigned long long n1) -> int {
         f.n_begin = n0; f.n_end = n1;
         SN_CUDA_CHECK(cudaMemsetAsync(f.next, 0, sizeof(unsigned long long), h->stream));
         const int sms = h->grid_limit > 0 ? std::min(h->grid_limit, h->num_sms) : h->num_sms;
         const int grid = (int)std::min<unsigned long long>(n1 - n0, (unsigned long long)sms);
-        if (h->species) sn_tiled_kernel<true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
-        else sn_tiled_kernel<false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
+        if (f.audit) {
+            if (h->species) sn_tiled_kernel<true, true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
+            else sn_tiled_kernel<false, true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
+        } else if (h->species) sn_tiled_kernel<true, false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
+        else sn_tiled_kernel<false, false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
         if (launches) (*launches)++;
         return SN_OK;
     };

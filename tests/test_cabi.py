@@ -78,3 +78,17 @@ def test_product_never_touches_the_oracle():
     for f in os.listdir(drv):
         text = open(os.path.join(drv, f), errors="ignore").read()
         assert "sn_oracle" not in text and "libref_" not in text, f
+
+
+def test_philox_known_answers_host_side(built):
+    """the counter-based generator against the Random123 known-answer vectors (host compilation
+    of the same __host__ __device__ function the kernels call; the device side is checked in test_gpu_audit.py)
+    and against an independent numpy implementation."""
+    import numpy as np
+    import starrynight_b200 as sn
+    from tests.helpers import PHILOX_KAT, philox4x32_10
+    host, _ = sn.philox_kat([list(c) + list(k) for c, k, _ in PHILOX_KAT])
+    assert np.array_equal(host, np.array([o for _, _, o in PHILOX_KAT], np.uint32))
+    rnd = np.random.default_rng(0).integers(0, 2 ** 32, size=(1000, 6), dtype=np.uint64).astype(np.uint32)
+    host, _ = sn.philox_kat(rnd)
+    assert np.array_equal(host, np.stack(philox4x32_10(*[rnd[:, i] for i in range(6)]), 1))
