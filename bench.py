@@ -4,17 +4,27 @@
 Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON
 line; for N > 1 it is launched under torchrun, one rank per GPU.
 
-Workload (BASELINE.json configs[4], the configuration the metric is quoted on):
+Default workload (BASELINE.json configs[4], the configuration the metric is quoted on):
 512^3 lattice, DipoleCutOff = 3, T = 300 K, CageStrain = 1, one species, seeded
 random start.  One "step" = SWEEPS_PER_STEP full-lattice sweeps (one attempt at
 every site per sweep).  At N > 1 the same lattice is Z-slab decomposed (strong
 scaling), halo planes pushed GPU-to-GPU over NVLink by the sweep kernel itself.
+``--workload c2|c3|c4|c5b`` measures the other BASELINE configurations through the
+same contract (see WORKLOADS); the default line is unchanged.
 
   value  whole-job attempts/s with the lattice resident in HBM (CUDA events on the
          library's own stream, max over ranks)
   e2e    the same metric through the C ABI with HOST buffers: every step uploads the
-         lattice from pinned host memory (sn_set_lattice), sweeps, and reads the
-         lattice and counters back (sn_get_lattice, sn_get_counters)
+         step's lattice from pinned host memory (sn_set_lattice_async), fills the slab
+         ghost planes device to device (sn_pull_ghosts), sweeps, and reads the lattice
+         and counters back (sn_get_lattice_async, sn_get_counters).  Successive steps
+         are independent batches, so two handles are used alternately: step i+1's
+         upload and step i-1's download travel over PCIe while step i is swept
+         (copies at PCIe rate cannot be hidden inside one 20-sweep step: 2 x 2.1 GB at
+         ~55 GB/s is 78 ms beside 115-145 ms of sweeps).  ``e2e.serial`` is the same
+         loop with one handle and synchronous calls.
+  state_hash  64-bit position-keyed hash of the final lattice bits of the
+         device-resident run: identical at every N iff the N-GPU chain is the 1-GPU chain
   roofline  FP32 CUDA-core roofline of the sweep kernel: algorithmic 2500 flop per
          attempt x attempts per launch / measured launch duration,
          against an FMA-peak microbenchmark run here (MEASURED_PEAKS.json has no FP32
@@ -50,34 +60,71 @@ SWEEPS_PER_STEP = 20
 T_KELVIN = 300
 
 
+WORKLOADS = {
+    # name: lattice, replicas per job, couplings; `slabs`: Z-slab decomposition at N > 1 (strong scaling), else the
+    # replicas are dealt out to the ranks (weak scaling: every GPU gets `replicas` of its own)
+    "c5": dict(what="512^3 lattice, DipoleCutOff=3, T=300 K, CageStrain=1, Efield=0, one species, random start (BASELINE.json configs[4])",
+               shape=(512, 512, 512), replicas=1, slabs=True, sweeps=20),
+    "c5b": dict(what="1024^3 lattice, DipoleCutOff=3, T=300 K, CageStrain=1, one species, random start (BASELINE.json configs[4], larger size)",
+                shape=(1024, 1024, 1024), replicas=1, slabs=True, sweeps=5),
+    "c2": dict(what="2-D 100x100x1 lattice, T=300 K, Efield=(0.02,0,0), DipoleCutOff=3 (28 neighbours), independent replicas/seeds "
+                    "(BASELINE.json configs[1]; starrynight.cfg:20)",
+               shape=(100, 100, 1), replicas=1184, slabs=False, sweeps=200, efield=(0.02, 0.0, 0.0)),
+    "c3": dict(what="64^3 lattice, DipoleCutOff=3, T = 0..500 K step 25 x CageStrain {0,1,2} = 63 replicas, one launch "
+                    "(BASELINE.json configs[2]; the reference's `superparallel` grid, Makefile:52-54)",
+               shape=(64, 64, 64), replicas=63, slabs=False, sweeps=40, temps=list(range(0, 501, 25)), cages=(0.0, 1.0, 2.0)),
+    "c4": dict(what="128^3 MA/FA solid solution: Dipoles=[1.0,0.5,0.0] Prevalence=[0.6,0.3,0.1] (two species + vacancies), triangular Efield.x "
+                    "ramp +-0.1 in 64 points, 1 sweep per point, 8 independent loops (seeds) (BASELINE.json configs[3])",
+               shape=(128, 128, 128), replicas=8, slabs=True, sweeps=64, species=((1.0, 0.5, 0.0), (0.6, 0.3, 0.1)), ramp=(0.1, 64)),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=512, help="lattice edge (default: the 512^3 headline config)")
-    ap.add_argument("--sweeps-per-step", type=int, default=SWEEPS_PER_STEP)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", type=int, default=None, help="lattice edge override for the cubic workloads")
+    ap.add_argument("--sweeps-per-step", type=int, default=None)
+    ap.add_argument("--replicas", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU sample for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident part only")
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    if a.size:
+        w["shape"] = (a.size, a.size, a.size if w["shape"][2] > 1 else 1)
+    if a.sweeps_per_step:
+        w["sweeps"] = a.sweeps_per_step
+    if a.replicas:
+        w["replicas"] = a.replicas
+    a.w = w
+    return a
+
+
+def flop_per_attempt(shape):
+    """20 N_nb + 6 N_nn + 24: 2500 for 3-D cut-off 3 (122 neighbours), 608 for Z == 1 (28)."""
+    nb, nn = (28, 4) if shape[2] == 1 else (122, 6)
+    return 20.0 * nb + 6.0 * nn + 24.0
 
 
 # ----------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
     """One process of the reference's replica-parallel mode: own lattice, own MT stream."""
-    size, sample_sites_z, moves, seed, use_ref = args
+    shape, moves, seed, use_ref, efield, species = args
     from oracle import oracle_api as oa
-    X = Y = size
-    Z = sample_sites_z
+    X, Y, Z = shape
     beta = 1.0 / (float(np.float32(T_KELVIN)) / 300.0)
-    p = oa.make_params(X, Y, Z, 3, 1.0, 0.0, (0.0, 0.0, 0.0), beta, 0, 3, T_KELVIN)
+    p = oa.make_params(X, Y, Z, 3, 1.0, 0.0, efield, beta, 0, 3, T_KELVIN)
+    lengths, prev = species if species else ([1.0, 0.0, 0.0], [1.0, 0.0, 0.0])
     if use_ref:
         r = oa.RefLib("f32")
         r.configure(p)
         r.seed(seed)
         r.initialise_lattice("random")               # lattice.c:25-37 through the reference's own code
-        r.solid_solution([1.0, 0.0, 0.0], [1.0, 0.0, 0.0])
+        r.solid_solution(list(lengths), list(prev))
         r.mc_moves(min(moves, 20000))                # touch the code path once
         t0 = time.perf_counter()
         r.mc_moves(moves)                            # MC_moves(int), montecarlo-core.c:143
@@ -86,7 +133,7 @@ def _cpu_worker(args):
         o = oa.Oracle("f32")
         mt = o.mt(seed)
         lat = o.initialise_lattice(p, mt, "random")
-        o.solid_solution(p, lat, mt, [1.0, 0.0, 0.0], [1.0, 0.0, 0.0])
+        o.solid_solution(p, lat, mt, list(lengths), list(prev))
         o.mc_moves(p, lat, mt, min(moves, 20000))
         t0 = time.perf_counter()
         o.mc_moves(p, lat, mt, moves)
@@ -94,64 +141,69 @@ def _cpu_worker(args):
     return moves, dt
 
 
-def cpu_reference_rate(size, seconds, procs=None):
+def cpu_reference_rate(w, seconds, procs=None):
     """Attempts/s of the reference CPU implementation on a bounded sample of the workload:
-    `procs` independent processes (the reference's only parallel mode), each running
-    MC_moves on a size x size x Zs random lattice, cut-off 3, T = 300.  Zs is the full
-    edge when memory allows, else the largest slab that fits (the chain's cost per attempt
-    is set by the cache-missing 122-neighbour gather, which a slab of >= 64 planes of a
-    512^2 cross-section -- 268 MB, far beyond any cache -- reproduces)."""
+    `procs` independent processes (the reference's only parallel mode, Makefile:49-63), each running
+    MC_moves on a lattice of the workload's cross-section, cut-off 3, T = 300.  The Z extent is the full
+    one when memory allows, else the largest slab that fits (the chain's cost per attempt is set by the
+    cache-missing 122-neighbour gather, which a slab of >= 64 planes of a 512^2 cross-section -- 268 MB,
+    far beyond any cache -- reproduces)."""
     import multiprocessing as mp
     from oracle import oracle_api as oa
     use_ref = oa.ref_available("f32")
     ncpu = os.cpu_count() or 1
     procs = procs or ncpu
+    X, Y, Z = w["shape"]
     try:
         avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
     except Exception:
         avail = 8 << 30
-    # reference allocates (16 B site) + pointer tables; python-side copies are not made in the ref path
-    per_plane = size * size * 16 * (1.0 if use_ref else 1.0)
-    zs = size
+    per_plane = X * Y * 16.0
+    zs = Z
     while zs > 64 and procs * zs * per_plane > 0.4 * avail:
         zs //= 2
     while procs > 1 and procs * zs * per_plane > 0.4 * avail:
         procs //= 2
-    rate_guess = 1.5e5                                # attempts/s/core at this size (BASELINE.md section 2)
+    rate_guess = 1.5e5 if X * Y * zs > 4e6 else 3.5e5 if Z > 1 else 1.5e6      # attempts/s/core (BASELINE.md section 2)
     moves = int(min(2 ** 31 - 1, max(2e5, rate_guess * seconds)))
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(size, zs, moves, 0xDEADBEEF + T_KELVIN + i, use_ref) for i in range(procs)])
+        res = pool.map(_cpu_worker, [((X, Y, zs), moves, 0xDEADBEEF + T_KELVIN + i, use_ref, tuple(w.get("efield", (0.0, 0.0, 0.0))),
+                                      w.get("species")) for i in range(procs)])
     wall = time.perf_counter() - t0
     total = sum(m for m, _ in res)
     slowest = max(dt for _, dt in res)
     rate = total / slowest
     return dict(value=rate, unit=UNIT, cores=procs, kind="reference" if use_ref else "port",
-                sample=f"{procs} independent processes x MC_moves({moves}) on a {size}x{size}x{zs} random lattice, "
+                sample=f"{procs} independent processes x MC_moves({moves}) on a {X}x{Y}x{zs} random lattice, "
                        f"cutoff 3, T=300 ({slowest:.1f} s of CPU work each; {wall:.1f} s wall incl. lattice init)",
-                per_core=rate / procs)
+                per_core=rate / procs, attempts=total, seconds=slowest)
 
 
 def run_reference(args):
+    """The reference's own CPU code on this box's cores.  A step here is the bounded sample itself: `attempts` moves
+    spread over all cores, timed by the slowest process -- ms_per_step is that measured time, not an extrapolation to
+    the GPU arm's step size (config.attempts_per_step); value = attempts / time is the rate the ratio is taken on."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t_all = time.perf_counter()
-    vals = []
+    vals, secs, atts = [], [], []
     info = None
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
-        info = cpu_reference_rate(args.size, per_step)
+        info = cpu_reference_rate(args.w, per_step)
         if i >= args.warmup:
-            vals.append(info["value"])
-    v = float(np.mean(vals))
-    attempts_per_step = args.sweeps_per_step * args.size ** 3
+            vals.append(info["value"]); secs.append(info["seconds"]); atts.append(info["attempts"])
+    v = float(np.sum(atts) / np.sum(secs))
+    cfg = workload_config(args, 1)
+    cfg["reference_step"] = {"attempts": float(np.mean(atts)), "note": "one step of this arm = one bounded sample (all cores), see cpu_baseline.sample"}
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * attempts_per_step / v, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "strong" if args.w["slabs"] else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
@@ -161,29 +213,34 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 def workload_config(args, n):
-    s = args.size
-    return {"workload": f"{s}^3 lattice, DipoleCutOff=3, T={T_KELVIN} K, CageStrain=1, Efield=0, one species, random start "
-                        f"(BASELINE.json configs[4])",
-            "lattice": [s, s, s], "cutoff": 3, "neighbours": 122, "sweeps_per_step": args.sweeps_per_step,
-            "attempts_per_step": args.sweeps_per_step * s ** 3, "decomposition": f"z-slabs x{n}" if n > 1 else "single GPU",
-            "l2": "lattice (2.1 GB at 512^3) exceeds the 126 MB L2; no flush needed"}
+    w = args.w
+    X, Y, Z = w["shape"]
+    reps = w["replicas"] * (1 if w["slabs"] else n)
+    nb = 28 if Z == 1 else 122
+    return {"workload": w["what"], "name": args.workload, "lattice": [X, Y, Z], "replicas": reps, "cutoff": 3, "neighbours": nb,
+            "sweeps_per_step": w["sweeps"], "attempts_per_step": w["sweeps"] * X * Y * Z * reps,
+            "decomposition": (f"z-slabs x{n}" if n > 1 else "single GPU") if w["slabs"] else f"{w['replicas']} replicas per GPU x{n}",
+            "l2": ("lattice (%.1f GB) exceeds the 126 MB L2; no flush needed" % (X * Y * Z * reps * 16 / 1e9)) if X * Y * Z * reps * 16 > 2e8
+                  else "working set fits in L2/shared memory by design (small lattices stay on chip); a 256 MB buffer is written between steps to flush L2"}
 
 
-def synthetic_slab(size, z0, nz, seed=1234):
-    """Seeded unit dipoles for planes [z0, z0+nz) of the size^3 lattice, reproducible plane by plane
+def synthetic_slab(shape, z0, nz, seed=1234, species=None):
+    """Seeded unit dipoles for planes [z0, z0+nz) of the lattice, reproducible plane by plane
     (any rank can generate any plane), generated on the GPU and returned in pinned host memory."""
     import torch
-    out = torch.empty((size, size, nz, 4), dtype=torch.float32, pin_memory=True)
+    X, Y, Z = shape
+    out = torch.empty((X, Y, nz, 4), dtype=torch.float32, pin_memory=True)
     dev = torch.device("cuda", torch.cuda.current_device())
 
     def s64(c):                                       # 64-bit constant as a signed int64
         return c - (1 << 64) if c >= (1 << 63) else c
 
-    ax = torch.arange(size, device=dev, dtype=torch.int64)
+    ax = torch.arange(X, device=dev, dtype=torch.int64)
+    ay = torch.arange(Y, device=dev, dtype=torch.int64)
     chunk = 64                                        # planes per batch: a handful of launches for the whole slab
     for c0 in range(0, nz, chunk):
-        zz = (torch.arange(c0, min(nz, c0 + chunk), device=dev, dtype=torch.int64) + z0) % size
-        idx = (ax[:, None, None] * size + ax[None, :, None]) * size + zz[None, None, :]
+        zz = (torch.arange(c0, min(nz, c0 + chunk), device=dev, dtype=torch.int64) + z0) % Z
+        idx = (ax[:, None, None] * Y + ay[None, :, None]) * Z + zz[None, None, :]
         # splitmix64 of (global site index, seed): the value of a site does not depend on who generates it
         h = idx * s64(0x9E3779B97F4A7C15) + seed
         h = (h ^ ((h >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
@@ -194,7 +251,14 @@ def synthetic_slab(size, z0, nz, seed=1234):
         cz = 1.0 - 2.0 * u1
         phi = 6.283185307179586 * u2
         r = torch.sqrt(torch.clamp(1.0 - cz * cz, min=0.0))
-        block = torch.stack([r * torch.cos(phi), r * torch.sin(phi), cz, torch.ones_like(cz)], -1)
+        if species:                                   # lengths by prevalence (solid_solution, lattice.c:139-165), from the low hash bits
+            lengths, prev = species
+            u3 = (h & 0xFF).to(torch.float32) * (1.0 / 256.0)
+            edges = torch.tensor(np.cumsum(prev) / np.sum(prev), device=dev, dtype=torch.float32)
+            ln = torch.tensor(lengths, device=dev, dtype=torch.float32)[torch.bucketize(u3, edges[:-1], right=True)]
+        else:
+            ln = torch.ones_like(cz)
+        block = torch.stack([r * torch.cos(phi), r * torch.sin(phi), cz, ln], -1)
         out[:, :, c0:c0 + block.shape[2], :].copy_(block)
         del idx, h, u1, u2, cz, phi, r, block
     torch.cuda.synchronize()
@@ -311,41 +375,71 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    size = args.size
-    if size % (32 * n):
-        raise SystemExit(f"lattice edge {size} must be a multiple of {32 * n} for {n} slabs")
-    nz = size // n
-    z0 = rank * nz
+    w = args.w
+    X, Y, Z = w["shape"]
+    slabs = w["slabs"] and n > 1
+    if slabs and Z % (32 * n):
+        raise SystemExit(f"Z = {Z} must be a multiple of {32 * n} for {n} slabs")
+    nz = Z // n if slabs else Z
+    z0 = rank * nz if slabs else 0
+    reps = w["replicas"]
     beta = sn.beta_of_T(T_KELVIN)
-    sim = sn.Simulation(size, size, size, DipoleCutOff=3, CageStrain=1.0, K=0.0, Efield=(0.0, 0.0, 0.0), beta=beta,
-                        seed=0xDEADBEEF + T_KELVIN, device=local, z0=z0 if n > 1 else 0, nz=nz if n > 1 else 0)
-    host = synthetic_slab(size, z0, nz)
-    host_out = torch.empty_like(host).pin_memory()
+    species = w.get("species")
+    seed0 = 0xDEADBEEF + T_KELVIN + (0 if w["slabs"] else 7919 * rank)      # replica workloads: every rank its own streams
 
-    ghosts = None
-    if n > 1:                                        # ghost planes: the neighbours' boundary planes, regenerated locally
-        ghosts = (synthetic_slab(size, (z0 - 3) % size, 3), synthetic_slab(size, (z0 + nz) % size, 3))
+    def make_sim():
+        sim = sn.Simulation(X, Y, Z, DipoleCutOff=3, CageStrain=1.0, K=0.0, Efield=tuple(w.get("efield", (0.0, 0.0, 0.0))), beta=beta,
+                            nreplicas=reps, seed=seed0, device=local, z0=z0 if slabs else 0, nz=nz if slabs else 0)
+        if "temps" in w:                              # T x CageStrain grid, one replica per point
+            grid = [(t, c) for c in w["cages"] for t in w["temps"]]
+            for r, (t, c) in enumerate(grid[:reps]):
+                sim.set_T(t, r)
+                sim.set_cagestrain(c, r)
+        return sim
 
-    def upload():
-        sim.set_lattice_ptr(host.data_ptr())
-        if n > 1:
-            sim.set_ghost(0, ghosts[0].numpy())
-            sim.set_ghost(1, ghosts[1].numpy())
+    def wire(sim):
+        if slabs:                                     # the NVLink path: CUDA IPC handles around the ring
+            handles = [None] * n
+            dist.all_gather_object(handles, sim.ipc_export())
+            sim.ipc_attach(0, *handles[(rank - 1) % n])
+            sim.ipc_attach(1, *handles[(rank + 1) % n])
 
-    upload()
-    if n > 1:                                        # wire the NVLink path: CUDA IPC handles around the ring
-        handles = [None] * n
-        dist.all_gather_object(handles, sim.ipc_export())
-        lo_r, hi_r = (rank - 1) % n, (rank + 1) % n
-        sim.ipc_attach(0, *handles[lo_r])
-        sim.ipc_attach(1, *handles[hi_r])
-        barrier()
+    hosts = [synthetic_slab(w["shape"], z0, nz, seed=1234 + 17 * r + (0 if w["slabs"] else 100003 * rank), species=species) for r in range(min(reps, 8))]
+    host_of = lambda r: hosts[r % len(hosts)]                         # replica workloads re-use 8 distinct start lattices
+    sim = make_sim()
+    wire(sim)
+    for r in range(reps):
+        sim.set_lattice_ptr(host_of(r).data_ptr(), r)
+    sim.pull_ghosts()
+    barrier()
 
-    spp = args.sweeps_per_step
-    attempts_step = spp * size ** 3                   # whole job
+    spp = w["sweeps"]
+    ramp = w.get("ramp")
+
+    def step(s, timed):
+        """One step's sweeps on handle s: (device ms, launches) when timed."""
+        if not ramp:
+            return s.MC_sweeps_timed(spp) if timed else (s.MC_sweeps(spp), 0)
+        amp, npts = ramp                              # hysteresis: triangular Efield.x ramp, spp / npts sweeps per point
+        ms = nl = 0.0
+        for k in range(npts):
+            ph = 4.0 * k / npts
+            e = amp * (ph if ph < 1 else 2 - ph if ph < 3 else ph - 4)
+            for r in range(reps):
+                s.set_efield((e, 0.0, 0.0), r)
+            if timed:
+                a, b = s.MC_sweeps_timed(max(1, spp // npts)); ms += a; nl += b
+            else:
+                s.MC_sweeps(max(1, spp // npts))
+        return ms, int(nl)
+
+    sites_job = X * Y * Z * reps * (1 if w["slabs"] else n)            # whole job
+    attempts_step = spp * sites_job
+    small = X * Y * Z * reps * 16 < 2e8
+    flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda") if small else None
     # ---- device-resident timing --------------------------------------------------------------
     for _ in range(args.warmup):
-        sim.MC_sweeps_timed(spp)
+        step(sim, True)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -353,8 +447,10 @@ def run_ours(args):
     ms_list, launches = [], 0
     t_wall = time.perf_counter()
     for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1.0)
         barrier()
-        ms, nl = sim.MC_sweeps_timed(spp)             # CUDA events on the library's stream
+        ms, nl = step(sim, True)                      # CUDA events on the library's stream
         ms_list.append(ms)
         launches += nl
     barrier()
@@ -369,30 +465,61 @@ def run_ours(args):
         ms_total = ms_local
     value = attempts_step * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers -------------------------------------
-    h2d = host.numel() * 4 + (sum(g.numel() * 4 for g in ghosts) if ghosts else 0)
-    d2h = host_out.numel() * 4 + 24
-    for _ in range(min(1, args.warmup)):
-        upload(); barrier(); sim.MC_sweeps(spp); sim.get_lattice_ptr(host_out.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        upload()                                      # H2D from pinned memory (slab + its ghost planes)
-        if n > 1:
-            barrier()                                 # neighbours' uploads done before anyone pushes ghosts
-        sim.MC_sweeps(spp)
-        sim.get_lattice_ptr(host_out.data_ptr())      # D2H (synchronises)
-        acc, rej, vac = sim.counters()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if n > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = attempts_step * args.steps / e2e_s
-    # lattice-wide observables of the final state, merged over the slabs by one FP64 all_reduce (sanity of the run)
+    # lattice-wide observables and content hash of the final state of the device-resident run
     from starrynight_b200 import slab as sn_slab
     merged = sn_slab.merge_observables(sim, dist if n > 1 else None, n, precision=sn.SN_PREC_F32)
+    hsh = sum(sim.state_hash(r) for r in range(reps)) % (1 << 64)
+    if n > 1:
+        parts = [None] * n
+        dist.all_gather_object(parts, hsh)
+        hsh = sum(parts) % (1 << 64)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        outs = [[torch.empty_like(host_of(r)).pin_memory() for r in range(reps)] for _ in range(2)]
+        h2d = sum(host_of(r).numel() * 4 for r in range(reps))
+        d2h = h2d + 24 * reps
+        sims = [sim, make_sim()]
+        wire(sims[1])
+
+        def e2e_loop(nsteps, pipelined):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(nsteps):
+                s, o = (sims[i % 2], sims[(i + 1) % 2]) if pipelined else (sims[0], None)
+                s.synchronize()                       # its previous download has landed: host buffers are free again
+                if i >= (2 if pipelined else 1):
+                    s.counters()                      # the step's result: ACCEPT / REJECT (and the lattice in outs)
+                for r in range(reps):
+                    s.set_lattice_async(host_of(r).data_ptr(), r)     # H2D from pinned memory
+                if o is not None:
+                    s.order_after(o)                  # the two handles' sweep kernels keep one order on every GPU
+                s.pull_ghosts()                       # slab ghost planes, device to device, handshake included
+                step(s, False)
+                for r in range(reps):
+                    s.get_lattice_async(outs[i % 2][r].data_ptr(), r)  # D2H
+            for s in (sims if pipelined else sims[:1]):
+                s.synchronize()
+                s.counters()
+            barrier()
+            dt = time.perf_counter() - t0
+            if n > 1:
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+
+        e2e_loop(2, True)                             # warm-up (staging buffers, pinned mappings)
+        dt_pipe = e2e_loop(args.steps, True)
+        e2e_loop(1, False)
+        dt_serial = e2e_loop(args.steps, False)
+        e2e = {"value": attempts_step * args.steps / dt_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d * n, "d2h_bytes_per_step": d2h * n,
+               "mode": "two handles used alternately: step i+1's upload and step i-1's download overlap step i's sweeps; every step's "
+                       "lattice is uploaded from and downloaded to pinned host memory inside the timed region",
+               "serial": {"value": attempts_step * args.steps / dt_serial, "mode": "one handle, each step upload -> sweeps -> download back to back"},
+               "seconds": dt_pipe}
+        sims[1].close()
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks = {}
@@ -402,17 +529,20 @@ def run_ours(args):
         pass
     hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     fp32_peak = sim.fp32_peak_tflops() if rank == 0 else None
-    sweep_launches = args.steps                      # one sn_tiled_kernel launch per sn_mc_sweeps call (all sweeps of a step);
-    #                                                  slab runs add signal + wait kernels around it (in `launches`)
-    avg_launch_ms = ms_local / max(1, sweep_launches)
-    attempts_per_launch = (size * size * nz) * spp * args.steps / max(1, sweep_launches)
-    achieved_tf = FLOP_PER_ATTEMPT * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e12
+    kern_id = sim.kernel_in_use()
+    kern_name = {sn.SN_KERNEL_TILED: "sn_tiled_kernel", sn.SN_KERNEL_RESIDENT: "sn_resident_kernel", sn.SN_KERNEL_COLOUR: "sn_colour_pass_kernel"}.get(kern_id, "?")
+    sweep_launches = max(1, args.steps * (ramp[1] if ramp else 1))     # one sweep-kernel launch per sn_mc_sweeps call (tiled / resident)
+    avg_launch_ms = ms_local / sweep_launches
+    attempts_per_launch = (X * Y * nz * reps) * spp * args.steps / sweep_launches
+    W = flop_per_attempt(w["shape"])
+    achieved_tf = W * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e12
     achieved_gbs = BYTES_PER_ATTEMPT * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e9
 
     traffic = None
     try:                                              # DRAM bytes per launch from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj["bytes_per_launch"] / tj["attempts_per_launch"] * attempts_per_launch
+        if kern_name == "sn_tiled_kernel":
+            traffic = tj["bytes_per_launch"] / tj["attempts_per_launch"] * attempts_per_launch
     except Exception:
         pass
     if rank == 0:
@@ -420,26 +550,31 @@ def run_ours(args):
         theo = 148 * 128 * 2 * sm_max * 1e6 / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if w["slabs"] else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * n, "d2h_bytes_per_step": d2h * n},
+            "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "sn_tiled_kernel", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp32", "kernel": kern_name, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp32_peak if fp32_peak else None,
+                         "basis": "ALGORITHMIC flops: the local-field form of site_energy costs 20 flop per neighbour (SURVEY.md 8d), "
+                                  "%d per attempt; the kernel executes fewer (pair symmetry and vanishing tensor entries: see "
+                                  "roofline.executed)" % int(W),
                          "peak_source": "FFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP32 entry)",
-                         "peak_theoretical": theo, "flop_per_attempt": FLOP_PER_ATTEMPT,
+                         "peak_theoretical": theo, "flop_per_attempt": W,
                          "attempts_per_launch": attempts_per_launch, "avg_launch_ms": avg_launch_ms,
+                         "executed": executed_roofline(kern_name, attempts_per_launch, avg_launch_ms, theo),
                          "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                                  "peak_source": hbm_src, "bytes_per_attempt": BYTES_PER_ATTEMPT},
                          "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write per launch, scaled by attempts per launch)"},
             "accept_ratio": merged["accept"] / max(1, merged["accept"] + merged["reject"]),
             "energy_per_site": float(merged["energy"].sum() / merged["nsites"]),
+            "state_hash": "%016x" % hsh,
             "wall_s_timed_region": t_wall,
         }
         if n == 1 and not args.no_cpu_baseline:
             try:
-                cb = cpu_reference_rate(size, args.cpu_seconds)
+                cb = cpu_reference_rate(w, args.cpu_seconds)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:                     # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
@@ -448,6 +583,21 @@ def run_ours(args):
     if n > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def executed_roofline(kernel, attempts_per_launch, avg_launch_ms, peak_tf):
+    """Pipe-level view beside the algorithmic roofline: FP32 instructions the kernel really executes per attempt
+    (ncu inst_executed_pipe_fma of the committed capture, profiles/traffic.json), each counted as one FMA = 2 flop."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if kernel != "sn_tiled_kernel" or "fp32_instr_per_attempt" not in tj:
+            return None
+        f = tj["fp32_instr_per_attempt"]
+        tf = 2.0 * f * attempts_per_launch / (avg_launch_ms * 1e-3) / 1e12
+        return {"fp32_instr_per_attempt": f, "achieved": tf, "unit": "TFLOP/s", "frac_of_theoretical": tf / peak_tf,
+                "source": tj.get("source", "profiles/traffic.json")}
+    except Exception:
+        return None
 
 
 def main():

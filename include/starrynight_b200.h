@@ -105,6 +105,14 @@ SN_API int sn_neighbour_table(sn_handle *h, int *n, int *dxyz, float *d);
  * float[X][Y][nz][4].  H2D / D2H copies happen inside the call. */
 SN_API int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen);
 SN_API int sn_get_lattice(sn_handle *h, int replica, float *xyzlen);
+/* The same, queued on the handle's stream without waiting: the buffer (pinned host memory, or the copy is not
+ * asynchronous) must stay untouched until sn_synchronize (or any synchronous call on the handle) returns.  With two
+ * handles used alternately, one lattice travels over PCIe while the other is being swept (see sn_order_after). */
+SN_API int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzlen);
+SN_API int sn_get_lattice_async(sn_handle *h, int replica, float *xyzlen);
+/* h's later work waits (on the device) for the sweeps queued so far on `other`: fixes the order of the two handles'
+ * persistent sweep kernels when they are used as a double buffer. */
+SN_API int sn_order_after(sn_handle *h, sn_handle *other);
 
 /* replaces assignments to the globals beta (main.c:215,239), Efield (config.c:132-134),
  * CageStrain (main.c:149) between MC_moves calls */
@@ -218,6 +226,10 @@ SN_API int sn_bench_fp32_peak(int device, double *tflops);
 SN_API int sn_get_boundary(sn_handle *h, int replica, int side, float *planes);
 /* side 0 = ghost planes below z0 (the lower neighbour's top planes), 1 = above */
 SN_API int sn_set_ghost(sn_handle *h, int replica, int side, const float *planes);
+/* device-to-device alternative to sn_get_boundary + sn_set_ghost: once every slab has its lattice (sn_set_lattice)
+ * and its neighbours (sn_ipc_attach / sn_attach_peer), each slab copies the neighbours' boundary planes into its
+ * ghost planes over NVLink, bracketed by the device-side handshake.  Stream-ordered; call it on every slab. */
+SN_API int sn_pull_ghosts(sn_handle *h);
 /* 64-byte CUDA IPC handles of the lattice buffer and the phase-flag buffer */
 SN_API int sn_ipc_export(sn_handle *h, void *lattice_handle64, void *flags_handle64);
 /* attach the neighbour that owns the planes below (side 0) / above (side 1) */

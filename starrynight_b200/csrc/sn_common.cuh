@@ -21,6 +21,8 @@
 #define SN_FLAGS_NEXT 32        // h->flags[32..33]: the tiled kernel's work counter (u64)
 #define SN_FLAGS_SPECIES 40     // h->flags[40]: result of the species scan in sn_set_lattice
 #define SN_FLAGS_ERR 44         // h->flags[44]: set by a device-side wait that ran out of time (a slab neighbour never arrived)
+#define SN_FLAGS_DESC 48        // h->flags[48..55]: slab descriptor (magic, X, Y, nz, replicas, cutoff, tiled, Z) checked by sn_ipc_attach
+#define SN_DESC_WORDS 8
 #define SN_FLAGS_VER 64         // h->flags[64..]: tile versions, [rep][X/16][Y/16][nz/16 + 2]
 #define SN_MAX_NB 1024          // neighbour-table capacity in constant memory (cutoff <= 6)
 
@@ -145,6 +147,7 @@ struct sn_handle {
     unsigned long long sweep = 0;       // sweeps done so far (Philox counter word)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};   // sn_mc_sweeps_timed
+    cudaEvent_t ev_sweeps = nullptr;          // recorded behind every sn_mc_sweeps (sn_order_after)
     int nnb = 0;
     std::vector<int> nb_dxyz;           // reference order (montecarlo-core.c:47-62)
     std::vector<float> nb_d;
@@ -155,6 +158,8 @@ struct sn_handle {
     std::vector<double> h_cage;         // CageStrain per replica, as given (device copy, rounded to float: efield[rep].w)
     bool species = true;                // false when every length is exactly 1 (skips the l_j multiplies)
     std::vector<char> rep_species;      // per replica: some length != 1
+    unsigned int *rep_species_dev = nullptr;   // device: raised by the upload kernel, read lazily (sn_resolve_species)
+    bool species_dirty = false;
     bool use_tiled = false;
     bool use_resident = false;          // lattice small enough to live in one CTA's shared memory (sn_sweep_resident.cuh)
     // The tiled kernel works on a second copy of the lattice whose z axis is de-interleaved by 4
@@ -189,6 +194,8 @@ int sn_tiled_prepare(sn_handle *h);
 void sn_tiled_release(sn_handle *h);
 int sn_refresh_ghosts(sn_handle *h);
 int sn_sync_canonical(sn_handle *h);
+int sn_convert_layout(sn_handle *h, bool to_tiled);
+int sn_resolve_species(sn_handle *h);
 int sn_energy_exact_launch(sn_handle *h, int replica, int precision, int n, const int *d_sites,
                            const float *d_newdip, double *d_out);
 int sn_energy_exact_map_launch(sn_handle *h, int replica, int precision, int which, double *d_out);

@@ -130,6 +130,12 @@ static int sn_push_couplings(sn_handle *h, int r)
     return SN_OK;
 }
 
+static void sn_slab_descriptor(const sn_handle *h, unsigned int d[SN_DESC_WORDS])
+{
+    d[0] = 0x534E3232u; d[1] = (unsigned)h->G.X; d[2] = (unsigned)h->G.Y; d[3] = (unsigned)h->G.nz; d[4] = (unsigned)h->p.nreplicas;
+    d[5] = (unsigned)h->p.cutoff; d[6] = h->use_tiled ? 1u : 0u; d[7] = (unsigned)h->G.Z;
+}
+
 static int sn_mode(const sn_handle *h) { return h->p.cutoff == 3 ? (h->p.Z == 1 ? 1 : 0) : 2; }
 
 // Everything sn_create does once the handle exists; any failure returns through sn_create, which destroys the
@@ -153,6 +159,9 @@ static int sn_create_body(sn_handle *h, const sn_params *p)
     h->num_sms = prop.multiProcessorCount;
     if (const char *t = getenv("SN_SPIN_TIMEOUT_S")) { const double v = atof(t); if (v > 0.0) h->spin_timeout_ns = (unsigned long long)(v * 1e9); }
     SN_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    SN_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_sweeps, cudaEventDisableTiming));
+    SN_CUDA_CHECK(cudaMalloc(&h->rep_species_dev, sizeof(unsigned int) * p->nreplicas));
+    SN_CUDA_CHECK(cudaMemsetAsync(h->rep_species_dev, 0, sizeof(unsigned int) * p->nreplicas, h->stream));
     const size_t cells = (size_t)G.rep_stride * p->nreplicas;
     if (cudaMalloc(&h->lat, cells * sizeof(float4)) != cudaSuccess) {
         cudaGetLastError();
@@ -206,6 +215,11 @@ static int sn_create_body(sn_handle *h, const sn_params *p)
         h->use_resident = can_reside && !h->use_tiled && (p->kernel == SN_KERNEL_AUTO || p->kernel == SN_KERNEL_RESIDENT);
     }
     if (h->use_tiled) { int rc = sn_tiled_prepare(h); if (rc) return rc; }
+    {
+        unsigned int d[SN_DESC_WORDS];
+        sn_slab_descriptor(h, d);
+        SN_CUDA_CHECK(cudaMemcpy(h->flags + SN_FLAGS_DESC, d, sizeof d, cudaMemcpyHostToDevice));
+    }
     if (!G.periodic_z) sn_slab_register(h, true);
     return SN_OK;
 }
@@ -252,6 +266,8 @@ extern "C" int sn_destroy(sn_handle *h)
     cudaFree(h->lat); cudaFree(h->beta); cudaFree(h->efield); cudaFree(h->counters); cudaFree(h->flags); cudaFree(h->rep_key);
     cudaFree(h->nb_table); cudaFree(h->d_nb_dxyz); cudaFree(h->d_scratch); cudaFree(h->staging);
     for (int e = 0; e < 2; e++) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
+    if (h->ev_sweeps) cudaEventDestroy(h->ev_sweeps);
+    cudaFree(h->rep_species_dev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SN_OK;
@@ -282,66 +298,132 @@ int sn_refresh_ghosts(sn_handle *h)
     return SN_OK;
 }
 
-// strided copy between the host's dense [X][Y][nz] float4 block and the padded device array
-__global__ void __launch_bounds__(256) sn_species_scan_kernel(const float4 *__restrict__ lat, const SnGeom G, unsigned int *__restrict__ flag)
+// ---- host <-> device lattice transfer ----------------------------------------------------------------
+// The host block is dense, float[X][Y][nz][4] (the reference's lattice[x][y][z]); on the device the lattice is
+// ghost-padded and, for the tiled kernel, de-interleaved in z.  A transfer is ONE contiguous copy between the host
+// block and a dense device staging buffer (full PCIe rate whatever the slab height) plus ONE kernel that moves
+// between staging and the layout the sweep kernel works on -- writing every periodic image on the way in, and
+// noting whether the replica carries species (any length != 1).  No strided copies, no separate ghost refresh, no
+// round trip through the canonical array, no host synchronisation.
+template <bool TILED>
+__global__ void __launch_bounds__(256) sn_scatter_kernel(const float4 *__restrict__ staging, float4 *__restrict__ dst, const SnGeom G,
+                                                         unsigned int *__restrict__ species_flag)
 {
-    const long long n = (long long)G.X * G.Y * G.nz;
+    // one thread per padded cell (ghost shell included); z ghosts of a Z-slab handle belong to the neighbours
+    // (sn_pull_ghosts / sn_set_ghost) and are left alone
+    const long long cells = (long long)(G.X + 2 * G.g) * G.PY * G.PZ;
     bool nonunit = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(i % G.nz), y = (int)((i / G.nz) % G.Y), x = (int)(i / ((long long)G.nz * G.Y));
-        nonunit |= lat[sn_pidx(G, x, y, z)].w != 1.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        const int zp = (int)(i % G.PZ) - G.gz, yp = (int)((i / G.PZ) % G.PY) - G.g, xp = (int)(i / ((long long)G.PZ * G.PY)) - G.g;
+        int xs = xp % G.X; xs += xs < 0 ? G.X : 0;
+        int ys = yp % G.Y; ys += ys < 0 ? G.Y : 0;
+        int zs = zp;
+        if (zp < 0 || zp >= G.nz) {
+            if (!G.periodic_z) continue;
+            zs = zp % G.nz; zs += zs < 0 ? G.nz : 0;
+        }
+        const float4 v = staging[((long long)xs * G.Y + ys) * G.nz + zs];
+        if (TILED) dst[sn_pidx2(G, xp, yp, zp)] = v; else dst[sn_pidx(G, xp, yp, zp)] = v;
+        nonunit |= (xs == xp && ys == yp && zs == zp && v.w != 1.0f);
     }
-    if (__any_sync(0xffffffffu, nonunit) && (threadIdx.x & 31) == 0) *flag = 1u;
+    if (__any_sync(0xffffffffu, nonunit) && (threadIdx.x & 31) == 0) *species_flag = 1u;
 }
 
-static int sn_copy_block(sn_handle *h, int replica, float *host, bool to_device)
+template <bool TILED>
+__global__ void __launch_bounds__(256) sn_gather_kernel(const float4 *__restrict__ src, float4 *__restrict__ staging, const SnGeom G)
 {
+    const long long n = (long long)G.X * G.Y * G.nz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i % G.nz), y = (int)((i / G.nz) % G.Y), x = (int)(i / ((long long)G.nz * G.Y));
+        staging[i] = TILED ? src[sn_pidx2(G, x, y, z)] : src[sn_pidx(G, x, y, z)];
+    }
+}
+
+static int sn_staging(sn_handle *h, float4 **out)
+{
+    const size_t bytes = (size_t)h->G.X * h->G.Y * h->G.nz * sizeof(float4);
+    if (bytes > h->staging_bytes) {
+        if (h->staging) cudaFree(h->staging);
+        h->staging = nullptr; h->staging_bytes = 0;
+        if (cudaMalloc(&h->staging, bytes) != cudaSuccess) { cudaGetLastError(); return sn_fail(SN_ERR_NOMEM, "cannot allocate %.1f MB of staging memory", bytes / 1e6); }
+        h->staging_bytes = bytes;
+    }
+    *out = (float4 *)h->staging;
+    return SN_OK;
+}
+
+// The species flags are raised on the device by the upload; the host looks at them only when it next has to
+// choose a kernel specialisation (sweep launch), so an upload never blocks.
+int sn_resolve_species(sn_handle *h)
+{
+    if (!h->species_dirty) return SN_OK;
+    std::vector<unsigned int> f(h->p.nreplicas);
+    SN_CUDA_CHECK(cudaMemcpyAsync(f.data(), h->rep_species_dev, sizeof(unsigned int) * h->p.nreplicas, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->species = false;
+    for (int r = 0; r < h->p.nreplicas; r++) { h->rep_species[r] = f[r] != 0; h->species = h->species || f[r] != 0; }
+    h->species_dirty = false;
+    return SN_OK;
+}
+
+extern "C" int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzlen)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_set_lattice: null buffer");
     const SnGeom &G = h->G;
-    cudaMemcpy3DParms c;
-    memset(&c, 0, sizeof c);
-    float4 *dev = h->lat + (long long)replica * G.rep_stride + sn_pidx(G, 0, 0, 0);
-    cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)G.nz * 16, (size_t)G.nz * 16, G.Y);
-    cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)G.PZ * 16, (size_t)G.PZ * 16, G.PY);
-    c.srcPtr = to_device ? hp : dp; c.dstPtr = to_device ? dp : hp;
-    c.extent = make_cudaExtent((size_t)G.nz * 16, G.Y, G.X);
-    c.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-    SN_CUDA_CHECK(cudaMemcpy3DAsync(&c, h->stream));
+    float4 *stg; int rc = sn_staging(h, &stg);
+    if (rc) return rc;
+    const size_t bytes = (size_t)G.X * G.Y * G.nz * sizeof(float4);
+    SN_CUDA_CHECK(cudaMemcpyAsync(stg, xyzlen, bytes, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaMemsetAsync(h->rep_species_dev + replica, 0, sizeof(unsigned int), h->stream));
+    const long long cells = G.rep_stride;
+    const int nblocks = (int)std::min<long long>((cells + 255) / 256, (long long)h->num_sms * 16);
+    if (h->use_tiled) {
+        // straight into the tiled kernel's copy; other replicas that only live in the canonical array come along first
+        if (!h->lat2_valid && h->p.nreplicas > 1 && (rc = sn_convert_layout(h, true))) return rc;
+        sn_scatter_kernel<true><<<nblocks, 256, 0, h->stream>>>(stg, h->lat2 + (long long)replica * sn_rep_stride2(G), G, h->rep_species_dev + replica);
+        h->lat2_valid = true; h->lat_valid = false;
+    } else {
+        if ((rc = sn_sync_canonical(h))) return rc;
+        sn_scatter_kernel<false><<<nblocks, 256, 0, h->stream>>>(stg, h->lat + (long long)replica * G.rep_stride, G, h->rep_species_dev + replica);
+        h->lat_valid = true; h->lat2_valid = false;
+    }
+    SN_CUDA_CHECK(cudaGetLastError());
+    h->species_dirty = true;
     return SN_OK;
 }
 
 extern "C" int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen)
 {
-    SN_CHECK_HANDLE(h, replica);
-    if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_set_lattice: null buffer");
-    int rc = sn_sync_canonical(h);                   // other replicas / ghost planes may only live in the tiled copy
+    int rc = sn_set_lattice_async(h, replica, xyzlen);
     if (rc) return rc;
-    h->lat2_valid = false;
-    if ((rc = sn_copy_block(h, replica, const_cast<float *>(xyzlen), true))) return rc;
-    if ((rc = sn_refresh_ghosts(h))) return rc;
-    // does any replica carry species (length != 1)?  decides the kernel specialisation (scanned on the device:
-    // a host loop over 512^3 sites costs more than the upload itself)
-    {
-        unsigned int nonunit = 0, *d_flag = h->flags + SN_FLAGS_SPECIES;
-        SN_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(unsigned int), h->stream));
-        sn_species_scan_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_flag);
-        SN_CUDA_CHECK(cudaGetLastError());
-        SN_CUDA_CHECK(cudaMemcpyAsync(&nonunit, d_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-        SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        h->rep_species[replica] = nonunit != 0;
-        h->species = false;
-        for (int r = 0; r < h->p.nreplicas; r++) h->species = h->species || h->rep_species[r];
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));      // the caller's buffer is free again
+    return SN_OK;
+}
+
+extern "C" int sn_get_lattice_async(sn_handle *h, int replica, float *xyzlen)
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_get_lattice: null buffer");
+    const SnGeom &G = h->G;
+    float4 *stg; int rc = sn_staging(h, &stg);
+    if (rc) return rc;
+    const long long n = (long long)G.X * G.Y * G.nz;
+    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 16);
+    if (h->use_tiled && h->lat2_valid) sn_gather_kernel<true><<<nblocks, 256, 0, h->stream>>>(h->lat2 + (long long)replica * sn_rep_stride2(G), stg, G);
+    else {
+        if ((rc = sn_sync_canonical(h))) return rc;
+        sn_gather_kernel<false><<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * G.rep_stride, stg, G);
     }
-    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    SN_CUDA_CHECK(cudaGetLastError());
+    SN_CUDA_CHECK(cudaMemcpyAsync(xyzlen, stg, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     return SN_OK;
 }
 
 extern "C" int sn_get_lattice(sn_handle *h, int replica, float *xyzlen)
 {
-    SN_CHECK_HANDLE(h, replica);
-    if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_get_lattice: null buffer");
-    int rc = sn_sync_canonical(h);
+    int rc = sn_get_lattice_async(h, replica, xyzlen);
     if (rc) return rc;
-    if ((rc = sn_copy_block(h, replica, xyzlen, false))) return rc;
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     return sn_check_device_error(h);
 }
@@ -443,14 +525,31 @@ static int sn_sweeps_impl(sn_handle *h, long long nsweeps, long long *launches)
     if (nsweeps < 0) return sn_fail(SN_ERR_INVALID, "sn_mc_sweeps: nsweeps %lld", nsweeps);
     if (!h->G.periodic_z && (!h->peer_lat[0] || !h->peer_lat[1]))
         return sn_fail(SN_ERR_INVALID, "sn_mc_sweeps: Z-slab handle has no neighbours attached (sn_ipc_attach / sn_attach_peer)");
-    if (h->use_resident) return sn_sweep_resident_launch(h, nsweeps, launches);
-    return h->use_tiled ? sn_sweep_tiled_launch(h, nsweeps, launches) : sn_sweep_colour_launch(h, nsweeps, launches);
+    { int rc = sn_resolve_species(h); if (rc) return rc; }
+    int rc;
+    if (h->use_resident) rc = sn_sweep_resident_launch(h, nsweeps, launches);
+    else rc = h->use_tiled ? sn_sweep_tiled_launch(h, nsweeps, launches) : sn_sweep_colour_launch(h, nsweeps, launches);
+    if (rc) return rc;
+    SN_CUDA_CHECK(cudaEventRecord(h->ev_sweeps, h->stream));     // sn_order_after
+    return SN_OK;
 }
 
 extern "C" int sn_mc_sweeps(sn_handle *h, long long nsweeps)
 {
     SN_CHECK_HANDLE(h, 0);
     return sn_sweeps_impl(h, nsweeps, nullptr);
+}
+
+// Make h's later work wait until the sweeps queued so far on `other` are done (device-side, the host does not block).
+// Two handles used as a double buffer -- one sweeping while the other's lattice is in flight over PCIe -- keep their
+// persistent sweep kernels in a fixed order this way (with Z-slabs on several GPUs every GPU must run them in the
+// same order, or the slabs would wait for each other across the two jobs).
+extern "C" int sn_order_after(sn_handle *h, sn_handle *other)
+{
+    SN_CHECK_HANDLE(h, 0);
+    if (!other) return sn_fail(SN_ERR_INVALID, "sn_order_after: null");
+    SN_CUDA_CHECK(cudaStreamWaitEvent(h->stream, other->ev_sweeps, 0));
+    return SN_OK;
 }
 
 extern "C" int sn_mc_sweeps_timed(sn_handle *h, long long nsweeps, double *ms, long long *launches)
@@ -482,7 +581,8 @@ extern "C" int sn_mc_sweep_audit(sn_handle *h, float *records)
     const size_t bytes = sizeof(float) * SN_AUDIT_WORDS * (size_t)h->p.nreplicas * h->G.X * h->G.Y * h->G.nz;
     float *dev = nullptr;
     if (cudaMalloc(&dev, bytes) != cudaSuccess) { cudaGetLastError(); return sn_fail(SN_ERR_NOMEM, "sn_mc_sweep_audit: cannot allocate %.1f MB", bytes / 1e6); }
-    int rc = SN_OK;
+    int rc = sn_resolve_species(h);
+    if (rc) { cudaFree(dev); return rc; }
     cudaError_t e = cudaMemsetAsync(dev, 0, bytes, h->stream);
     if (e == cudaSuccess) {
         h->audit_dev = dev;

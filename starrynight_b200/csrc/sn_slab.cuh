@@ -85,6 +85,58 @@ extern "C" int sn_set_ghost(sn_handle *h, int replica, int side, const float *pl
     return SN_OK;
 }
 
+// Fill my z ghost planes (x / y ghost columns included) from the neighbours' boundary planes, device to device.
+template <bool TILED>
+__global__ void __launch_bounds__(256) sn_pull_ghosts_kernel(float4 *__restrict__ mine, const float4 *__restrict__ lo, const float4 *__restrict__ hi,
+                                                             const SnGeom G, const long long rep_stride, const int nrep)
+{
+    const int PX = G.X + 2 * G.g;
+    const long long per_rep = (long long)PX * G.PY * 2 * G.gz, total = per_rep * nrep;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int rep = (int)(i / per_rep);
+        long long r = i - (long long)rep * per_rep;
+        const int dz = (int)(r % G.gz); r /= G.gz;
+        const int side = (int)(r & 1); r >>= 1;
+        const int yp = (int)(r % G.PY) - G.g, xp = (int)(r / G.PY) - G.g;
+        const int zdst = side == 0 ? dz - G.gz : G.nz + dz;              // my ghost plane
+        const int zsrc = side == 0 ? G.nz - G.gz + dz : dz;              // the same plane among the neighbour's own
+        const float4 *src = (side == 0 ? lo : hi) + (long long)rep * rep_stride;
+        float4 *dst = mine + (long long)rep * rep_stride;
+        if (TILED) dst[sn_pidx2(G, xp, yp, zdst)] = src[sn_pidx2(G, xp, yp, zsrc)];
+        else dst[sn_pidx(G, xp, yp, zdst)] = src[sn_pidx(G, xp, yp, zsrc)];
+    }
+}
+
+// After every slab of the lattice has been uploaded (sn_set_lattice) and wired (sn_ipc_attach / sn_attach_peer):
+// each slab copies its neighbours' boundary planes into its own ghost planes over NVLink.  Bracketed by the
+// device-side handshake: nobody reads a neighbour before that neighbour's upload has landed, nobody sweeps (and
+// changes its boundary) before its neighbours have read it.  Stream-ordered; call it on every slab.
+extern "C" int sn_pull_ghosts(sn_handle *h)
+{
+    SN_CHECK_HANDLE(h, 0);
+    if (h->G.periodic_z) return SN_OK;                 // the handle owns the whole axis: its ghosts are its own images
+    if (!h->peer_lat[0] || !h->peer_lat[1]) return sn_fail(SN_ERR_INVALID, "sn_pull_ghosts: no neighbours attached (sn_ipc_attach / sn_attach_peer)");
+    int rc;
+    if (h->use_tiled) {
+        if (!h->lat2_valid) {                          // neighbours read the tiled copy: bring it up to date first
+            if ((rc = sn_sync_canonical(h)) || (rc = sn_convert_layout(h, true))) return rc;
+            h->lat2_valid = true;
+        }
+    } else if ((rc = sn_sync_canonical(h))) return rc;
+    if ((rc = sn_slab_phase_sync(h, nullptr))) return rc;
+    const long long total = (long long)(h->G.X + 2 * h->G.g) * h->G.PY * 2 * h->G.gz * h->p.nreplicas;
+    const int nblocks = (int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8);
+    if (h->use_tiled) {
+        sn_pull_ghosts_kernel<true><<<nblocks, 256, 0, h->stream>>>(h->lat2, h->peer_lat[0], h->peer_lat[1], h->G, sn_rep_stride2(h->G), h->p.nreplicas);
+        h->lat_valid = false;
+    } else {
+        sn_pull_ghosts_kernel<false><<<nblocks, 256, 0, h->stream>>>(h->lat, h->peer_lat[0], h->peer_lat[1], h->G, h->G.rep_stride, h->p.nreplicas);
+        h->lat2_valid = false;
+    }
+    SN_CUDA_CHECK(cudaGetLastError());
+    return sn_slab_phase_sync(h, nullptr);
+}
+
 extern "C" int sn_ipc_export(sn_handle *h, void *lattice_handle64, void *flags_handle64)
 {
     SN_CHECK_HANDLE(h, 0);
@@ -113,6 +165,18 @@ extern "C" int sn_ipc_attach(sn_handle *h, int side, const void *lattice_handle6
     void *pl = nullptr, *pf = nullptr;
     SN_CUDA_CHECK(cudaIpcOpenMemHandle(&pl, a, cudaIpcMemLazyEnablePeerAccess));
     SN_CUDA_CHECK(cudaIpcOpenMemHandle(&pf, b, cudaIpcMemLazyEnablePeerAccess));
+    {
+        // the kernels index the neighbour's arrays with MY geometry: refuse a neighbour of another shape or kernel
+        unsigned int theirs[SN_DESC_WORDS], mine[SN_DESC_WORDS];
+        sn_slab_descriptor(h, mine);
+        SN_CUDA_CHECK(cudaMemcpy(theirs, (unsigned int *)pf + SN_FLAGS_DESC, sizeof theirs, cudaMemcpyDefault));
+        if (memcmp(theirs, mine, sizeof mine)) {
+            cudaIpcCloseMemHandle(pl); cudaIpcCloseMemHandle(pf);
+            return sn_fail(SN_ERR_INVALID, "sn_ipc_attach: the neighbour is not a slab of the same decomposition (X,Y,nz,replicas,cutoff,kernel = "
+                                           "%u,%u,%u,%u,%u,%u here, %u,%u,%u,%u,%u,%u there)", mine[1], mine[2], mine[3], mine[4], mine[5], mine[6],
+                           theirs[1], theirs[2], theirs[3], theirs[4], theirs[5], theirs[6]);
+        }
+    }
     h->peer_lat[side] = (float4 *)pl; h->peer_flags[side] = (unsigned int *)pf; h->peer_is_ipc[side] = true;
     memcpy(h->ipc_key[side], lattice_handle64, 64);
     return SN_OK;

@@ -428,6 +428,9 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                          ::"r"(dst), "l"(&tmap), "r"(it.z0), "r"(r), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
         }
     };
+    // Block-wide rendezvous of the control warp and the workers.  They meet from different places in the code, so this
+    // is a named barrier with an explicit thread count (bar.sync 2, THREADS), not __syncthreads().
+    auto cta_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(snt::THREADS) : "memory"); };
     // ---- control warp -----------------------------------------------------------------------------
     auto deps_met = [&]() {
         // The halo was written by other CTAs / GPUs through the generic proxy and observed by this warp's
@@ -464,7 +467,8 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             if (lane == 0) issue_tile_load(cur);
         }
         if (lane == 0) *ctl_item = cur;
-        __syncthreads();
+        __syncwarp();
+        cta_sync();
         for (unsigned int done = 8; cur.valid; done += 8) {
             // while the workers compute `cur`: next item, first look at its dependencies
             SnTileItem nxt = take();
@@ -476,7 +480,8 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             if (ready) deps_met();
             nxt.ready = ready;
             if (lane == 0) *ctl_item = nxt;
-            __syncthreads();                              // hand-over: every worker has read its part of the tile
+            __syncwarp();
+            cta_sync();                                   // hand-over: every worker has read its part of the tile
             if (ready && lane == 0) issue_tile_load(nxt);
             while ((int)(*reinterpret_cast<volatile unsigned int *>(ctl_arrive) - done) < 0) __nanosleep(40);
             __syncwarp();
@@ -493,7 +498,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
 
     // ---- workers -----------------------------------------------------------------------------------
     auto workers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(snt::WORKERS) : "memory"); };
-    __syncthreads();
+    cta_sync();
     SnTileItem item = *ctl_item;
 
     while (item.valid) {
@@ -603,6 +608,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
                     cg[s] = make_float3(-tm.cage * dpp[s].x, -tm.cage * dpp[s].y, -tm.cage * dpp[s].z);
                 }
                 float3 dmS[4], dpS[4], dmU[4], dpU[4];
+                __syncwarp();      // every lane has read its own column (which holds its neighbours' segments) before any lane's chain writes
 #ifdef SN_EXP_NOCHAIN
 #pragma unroll
                 for (int t4 = 0; t4 < 0; t4++) {
@@ -681,7 +687,8 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             }
             __syncwarp();
             if (lane == 0) atomicAdd(ctl_wbread, 1u);     // tells the control warp to stop polling and come to the hand-over
-            __syncthreads();                              // hand-over: the control warp starts the next TMA load
+            __syncwarp();
+            cta_sync();                                   // hand-over: the control warp starts the next TMA load
             nxt = *ctl_item;
             const long long gbase = sn_pidx2(G, x0, y0, z0 + lz);
             const long long sy2 = 4LL * sn_q2(G), sx2 = sy2 * G.PY;
@@ -771,7 +778,7 @@ void sn_tiled_release(sn_handle *h)
     h->lat2 = nullptr;
 }
 
-static int sn_convert_layout(sn_handle *h, bool to_tiled)
+int sn_convert_layout(sn_handle *h, bool to_tiled)
 {
     dim3 grid((unsigned)((h->G.rep_stride + 255) / 256), h->p.nreplicas);
     sn_convert_layout_kernel<<<grid, 256, 0, h->stream>>>(h->lat, h->lat2, h->G, to_tiled ? 1 : 0);

@@ -38,13 +38,11 @@ def exchange_ghosts(sim, dist, world: int, rank: int, replica: int = 0):
     My lowest planes become the lower neighbour's upper ghost, my highest planes the
     upper neighbour's lower ghost."""
     import torch
+    if world == 1:
+        return                                        # the handle owns the whole axis: its ghosts are its own periodic images
     lo, hi = ring_neighbours(world, rank)
     mine_low = torch.from_numpy(np.ascontiguousarray(sim.get_boundary(0, replica)))
     mine_high = torch.from_numpy(np.ascontiguousarray(sim.get_boundary(1, replica)))
-    if world == 1:
-        sim.set_ghost(0, mine_high.numpy(), replica)
-        sim.set_ghost(1, mine_low.numpy(), replica)
-        return
     got = [torch.empty_like(mine_low) for _ in range(2 * world)]
     # all_gather keeps the exchange deadlock-free on every backend (2 small tensors per rank)
     dist.all_gather(got[:world], mine_low)

@@ -112,7 +112,7 @@ def _replay(p, lat0, rec, final, what):
         de_gpu = rec[sx, sy, sz, 4].astype(np.float64)
         dec = rec[sx, sy, sz, 5] == 1.0
         de_ref = o64.site_energy(p, lat, sites, nd)                      # the reference's site_energy, at this point of the chain
-        scale = term_scale_batch(p, lat, sites, nd, dxyz, d)
+        scale = np.maximum(term_scale_batch(p, lat, sites, nd, dxyz, d), 1e-3)   # a ConstrainToX trial may equal the old dipole: every term 0
         err = np.abs(de_gpu - de_ref) / scale
         worst = max(worst, float(err.max()))
         assert err.max() < 1e-5, f"{what}: group {g}: |dE_gpu - dE_ref| / sum|terms| = {err.max():.3g}"

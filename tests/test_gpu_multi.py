@@ -26,7 +26,7 @@ def devices():
     return list(range(min(n, 8))) if n >= 2 else [0]
 
 
-def _run_split(sn, lat, nslab, kernel, sweeps, devices, per_call=1):
+def _run_split(sn, lat, nslab, kernel, sweeps, devices, per_call=1, pull=True):
     X, Y, Z = lat.shape[:3]
     nz = Z // nslab
     sims = [sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.05, 0, 0), seed=99, device=devices[r % len(devices)], z0=r * nz, nz=nz, kernel=kernel)
@@ -35,10 +35,14 @@ def _run_split(sn, lat, nslab, kernel, sweeps, devices, per_call=1):
         s.set_lattice(lat[:, :, r * nz:(r + 1) * nz])
     for r, s in enumerate(sims):
         lo, hi = sims[(r - 1) % nslab], sims[(r + 1) % nslab]
-        s.set_ghost(0, lo.get_boundary(1))
-        s.set_ghost(1, hi.get_boundary(0))
+        if not pull:                                   # bootstrap through the host (sn_get_boundary / sn_set_ghost)
+            s.set_ghost(0, lo.get_boundary(1))
+            s.set_ghost(1, hi.get_boundary(0))
         s.attach_peer(0, lo)
         s.attach_peer(1, hi)
+    if pull:                                           # device to device (sn_pull_ghosts), every slab
+        for s in sims:
+            s.pull_ghosts()
     for _ in range(sweeps // per_call):     # few sweeps per call per slab: the launch queues never fill
         for s in sims:
             s.MC_sweeps(per_call)
@@ -65,6 +69,8 @@ def test_two_slabs_match_one_gpu_bit_for_bit(sn, devices, shape, kernel):
         ref_h = one.state_hash()
     out, counters, energy = _run_split(sn, lat, 2, kid, 3, devices=devices)
     assert np.array_equal(out, ref), "slab-decomposed chain differs from the single-GPU chain"
+    out_h, _, _ = _run_split(sn, lat, 2, kid, 3, devices=devices, pull=False)
+    assert np.array_equal(out_h, ref), "ghost planes set through the host give a different chain"
     assert _run_split.last_hash == ref_h, "the slabs' state hashes do not add up to the single-GPU hash"
     assert np.array_equal(counters, ref_c)
     assert np.allclose(energy, ref_e, rtol=1e-12, atol=1e-9)

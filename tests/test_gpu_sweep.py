@@ -416,3 +416,36 @@ def test_full_size_lattice_invariants(sn):
         P = sim.polarisation()
         assert np.all(np.abs(P) < 0.01)                # no net polarisation from a random start after 2 sweeps
     del lat, out
+
+
+@pytest.mark.parametrize("shape,kernel", [((64, 32, 32), "auto"), ((20, 20, 28), "auto"), ((24, 16, 20), "colour")])
+def test_async_double_buffer_equals_synchronous_calls(sn, shape, kernel):
+    """sn_set_lattice_async / sn_get_lattice_async / sn_order_after: two handles used alternately (one lattice in flight
+    over PCIe while the other is swept) give exactly what synchronous calls on one handle give."""
+    import torch
+    X, Y, Z = shape
+    lats = [oa.random_lattice(X, Y, Z, seed=50 + i, lengths=(1.0, 0.5, 0.0), prevalence=(0.7, 0.2, 0.1)) for i in range(4)]
+    lats[1][..., 3] = 1.0                              # one batch without species: the kernel specialisation must follow the data
+    want = []
+    with sn.Simulation(X, Y, Z, CageStrain=1.0, seed=3, kernel=kernel_id(sn, kernel)) as one:
+        for lat in lats:
+            one.set_lattice(lat)
+            one.set_sweep_count(0)
+            one.MC_sweeps(2)
+            want.append(one.get_lattice())
+    sims = [sn.Simulation(X, Y, Z, CageStrain=1.0, seed=3, kernel=kernel_id(sn, kernel)) for _ in range(2)]
+    src = [torch.from_numpy(l).pin_memory() for l in lats]
+    dst = [torch.empty((X, Y, Z, 4), dtype=torch.float32).pin_memory() for _ in lats]
+    for i in range(4):
+        s, o = sims[i % 2], sims[(i + 1) % 2]
+        s.synchronize()
+        s.set_sweep_count(0)
+        s.set_lattice_async(src[i].data_ptr())
+        s.order_after(o)
+        s.MC_sweeps(2)
+        s.get_lattice_async(dst[i].data_ptr())
+    for s in sims:
+        s.synchronize()
+        s.close()
+    for i in range(4):
+        assert np.array_equal(dst[i].numpy(), want[i]), f"batch {i}"
