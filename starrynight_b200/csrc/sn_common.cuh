@@ -200,4 +200,5 @@ int sn_energy_exact_launch(sn_handle *h, int replica, int precision, int n, cons
                            const float *d_newdip, double *d_out);
 int sn_energy_exact_map_launch(sn_handle *h, int replica, int precision, int which, double *d_out);
 int sn_scratch(sn_handle *h, size_t bytes, void **out);
+int sn_energy_exact_preload();
 int sn_check_device_error(sn_handle *h);

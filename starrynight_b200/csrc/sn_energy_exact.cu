@@ -125,3 +125,15 @@ int sn_energy_exact_map_launch(sn_handle *h, int replica, int precision, int whi
     SN_CUDA_CHECK(cudaGetLastError());
     return SN_OK;
 }
+
+// see sn_preload_kernels (sn_lib.cu)
+int sn_energy_exact_preload()
+{
+    const void *kernels[] = {(const void *)sn_site_energy_exact_kernel<double>, (const void *)sn_site_energy_exact_kernel<float>,
+                             (const void *)sn_interaction_map_exact_kernel<double>, (const void *)sn_interaction_map_exact_kernel<float>};
+    for (const void *k : kernels) {
+        cudaFuncAttributes a;
+        SN_CUDA_CHECK(cudaFuncGetAttributes(&a, k));
+    }
+    return SN_OK;
+}

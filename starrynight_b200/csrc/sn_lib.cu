@@ -56,8 +56,9 @@ int sn_check_device_error(sn_handle *h)
     unsigned int e = 0;
     SN_CUDA_CHECK(cudaMemcpyAsync(&e, h->flags + SN_FLAGS_ERR, sizeof e, cudaMemcpyDeviceToHost, h->stream));
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    if (e) return sn_fail(SN_ERR_CUDA, "a device-side wait timed out after %.1f s: a Z-slab neighbour never ran its part of the sweep "
-                                       "(results of this handle are invalid)", h->spin_timeout_ns * 1e-9);
+    if (e) return sn_fail(SN_ERR_CUDA, "a device-side wait timed out after %.1f s (%s): a Z-slab neighbour never ran its part of the sweep "
+                                       "(results of this handle are invalid)", h->spin_timeout_ns * 1e-9,
+                          e == 2 ? "tile dependencies of the sweep kernel" : "slab handshake");
     return SN_OK;
 }
 
@@ -138,6 +139,8 @@ static void sn_slab_descriptor(const sn_handle *h, unsigned int d[SN_DESC_WORDS]
 
 static int sn_mode(const sn_handle *h) { return h->p.cutoff == 3 ? (h->p.Z == 1 ? 1 : 0) : 2; }
 
+static int sn_preload_kernels(int device);
+
 // Everything sn_create does once the handle exists; any failure returns through sn_create, which destroys the
 // partially built handle (stream, device buffers, registry entry) -- no early return leaks.
 static int sn_create_body(sn_handle *h, const sn_params *p)
@@ -157,6 +160,7 @@ static int sn_create_body(sn_handle *h, const sn_params *p)
     cudaDeviceProp prop;
     SN_CUDA_CHECK(cudaGetDeviceProperties(&prop, p->device));
     h->num_sms = prop.multiProcessorCount;
+    { int rc = sn_preload_kernels(p->device); if (rc) return rc; }
     if (const char *t = getenv("SN_SPIN_TIMEOUT_S")) { const double v = atof(t); if (v > 0.0) h->spin_timeout_ns = (unsigned long long)(v * 1e9); }
     SN_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     SN_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_sweeps, cudaEventDisableTiming));
@@ -1043,3 +1047,43 @@ extern "C" int sn_bench_fp32_peak(int device, double *tflops)
 }
 
 #include "sn_slab.cuh"
+
+// CUDA loads kernels lazily, and loading one can need a context-wide synchronisation.  A slab's stream may hold a
+// kernel that spins until a neighbouring slab has launched something (handshake, tile versions); if that something
+// is launched for the first time in the process while the spinner runs, the load waits for the spinner and the
+// spinner for the launch.  So every kernel of the library is loaded up front, once per device.
+static int sn_preload_kernels(int device)
+{
+    static std::mutex m;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lock(m);
+    if (std::find(done.begin(), done.end(), device) != done.end()) return SN_OK;
+    const void *kernels[] = {
+        (const void *)sn_phase_signal_kernel, (const void *)sn_phase_wait_kernel,
+        (const void *)sn_pull_ghosts_kernel<true>, (const void *)sn_pull_ghosts_kernel<false>,
+        (const void *)sn_scatter_kernel<true>, (const void *)sn_scatter_kernel<false>,
+        (const void *)sn_gather_kernel<true>, (const void *)sn_gather_kernel<false>,
+        (const void *)sn_convert_layout_kernel, (const void *)sn_refresh_ghosts_kernel, (const void *)sn_fill_u32_kernel,
+        (const void *)sn_tiled_kernel<true, false>, (const void *)sn_tiled_kernel<false, false>,
+        (const void *)sn_tiled_kernel<true, true>, (const void *)sn_tiled_kernel<false, true>,
+        (const void *)sn_colour_pass_kernel<0, true>, (const void *)sn_colour_pass_kernel<0, false>,
+        (const void *)sn_colour_pass_kernel<1, true>, (const void *)sn_colour_pass_kernel<1, false>,
+        (const void *)sn_colour_pass_kernel<2, true>,
+        (const void *)sn_resident_kernel<0, true>, (const void *)sn_resident_kernel<0, false>,
+        (const void *)sn_resident_kernel<1, true>, (const void *)sn_resident_kernel<1, false>, (const void *)sn_resident_kernel<2, true>,
+        (const void *)sn_sum_dipoles_kernel, (const void *)sn_state_hash_kernel, (const void *)sn_sum_doubles_kernel,
+        (const void *)sn_energy_f32_kernel<0, true>, (const void *)sn_energy_f32_kernel<1, true>, (const void *)sn_energy_f32_kernel<2, true>,
+        (const void *)sn_site_energy_f32_kernel<0, true>, (const void *)sn_site_energy_f32_kernel<1, true>, (const void *)sn_site_energy_f32_kernel<2, true>,
+        (const void *)sn_rdf_kernel<true>, (const void *)sn_rdf_kernel<false>, (const void *)sn_potential_kernel<true>, (const void *)sn_potential_kernel<false>,
+        (const void *)sn_efield_kernel<true>, (const void *)sn_efield_kernel<false>, (const void *)sn_recombination_kernel,
+    };
+    for (const void *k : kernels) {
+        cudaFuncAttributes a;
+        SN_CUDA_CHECK(cudaFuncGetAttributes(&a, k));
+    }
+    int rc = sn_energy_exact_preload();
+    if (rc) return rc;
+    done.push_back(device);
+    return SN_OK;
+}
+

@@ -27,7 +27,11 @@ __global__ void sn_phase_wait_kernel(unsigned int *flags, unsigned int epoch, un
         for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + s) : "memory");
             if ((int)(v - epoch) >= 0) break;
-            if (sn_globaltimer_ns() - t0 > timeout_ns) { atomicExch(flags + SN_FLAGS_ERR, 1u); return; }   // the neighbour never arrived
+            if (sn_globaltimer_ns() - t0 > timeout_ns) {                   // the neighbour never arrived
+                printf("starrynight_b200: slab handshake timed out: waiting for epoch %u, neighbour %s is at %u\n", epoch, s ? "above" : "below", v);
+                atomicExch(flags + SN_FLAGS_ERR, 1u);
+                return;
+            }
             __nanosleep(200);
         }
     }

@@ -430,7 +430,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     };
     // Block-wide rendezvous of the control warp and the workers.  They meet from different places in the code, so this
     // is a named barrier with an explicit thread count (bar.sync 2, THREADS), not __syncthreads().
-    auto cta_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(snt::THREADS) : "memory"); };
+    auto cta_sync = [&]() { asm volatile("barrier.sync 2, %0;" ::"n"(snt::THREADS) : "memory"); };
     // ---- control warp -----------------------------------------------------------------------------
     auto deps_met = [&]() {
         // The halo was written by other CTAs / GPUs through the generic proxy and observed by this warp's
@@ -454,7 +454,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         while (!sn_tile_deps_ready(fl, it, lane)) {
             __nanosleep(100);
             if (sn_globaltimer_ns() - t0 > fl.timeout_ns || *reinterpret_cast<volatile unsigned int *>(fl.err)) {
-                if (lane == 0) atomicExch(fl.err, 1u);
+                if (lane == 0) atomicExch(fl.err, 2u);
                 break;
             }
         }
