@@ -194,7 +194,12 @@ SN_API int sn_state_hash(sn_handle *h, int replica, unsigned long long *hash);
 SN_API int sn_kernel_in_use(sn_handle *h, int *kernel);
 /* replaces landau_order() (analysis.c:506-526): |sum_i p_i|^2 / N * N as written there */
 SN_API int sn_landau_order(sn_handle *h, int replica, double *landau);
-/* replaces radial_order_parameter() (analysis.c:528-598): accumulated sums and
+/* Observables on a Z-slab handle cover the handle's own sites; planes beyond the slab are read from the neighbouring
+ * GPUs over NVLink (the slab must be at least as high as the stencil radius: 9 for the RDF, 6 for the potential).
+ * Sums (sn_rdf, sn_total_energy, sn_polarisation x sites, sn_recombination_partial) add up over the slabs; maps are
+ * per slab.  Call them on every slab between the same two sweeps.
+ *
+ * replaces radial_order_parameter() (analysis.c:528-598): accumulated sums and
  * counts per r^2 = 0..80 BEFORE the division at :587-588, in FP64 / int64 */
 SN_API int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum, long long *count);
 /* replaces dipole_potential() over the lattice (analysis.c:65-94,264-308): V[X][Y][nz] */
@@ -207,6 +212,11 @@ SN_API int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_offset,
  * FD-Total-electron FD-Total-hole eMAX hMAX RMAX */
 #define SN_RECOMB_N 11
 SN_API int sn_recombination(sn_handle *h, int replica, double out[SN_RECOMB_N]);
+/* the same in two halves for a Z-slab decomposed lattice: the partial sums over one handle's own sites (5 partition /
+ * occupation sums, 3 maxima over the global z = 0 plane, the site count), then the normalisations over all slabs */
+#define SN_RECOMB_PARTIAL_N 9
+SN_API int sn_recombination_partial(sn_handle *h, int replica, double part[SN_RECOMB_PARTIAL_N]);
+SN_API int sn_recombination_finish(int nparts, const double *parts, double out[SN_RECOMB_N]);
 
 /* Test aid: Philox4x32-10 (Salmon et al., SC'11), the counter-based generator that replaces the reference's global
  * MT19937 stream (mt19937ar-cok.c; montecarlo-core.c:159-161,179), evaluated for n inputs of 6 words

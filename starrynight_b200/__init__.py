@@ -30,7 +30,7 @@ EXPORTS = [
     "sn_set_lattice", "sn_get_lattice", "sn_set_lattice_async", "sn_get_lattice_async", "sn_order_after", "sn_pull_ghosts", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_set_replica_cagestrain", "sn_mc_sweeps", "sn_mc_sweep_audit",
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_set_counters",
     "sn_get_sweep_count", "sn_set_sweep_count", "sn_set_replica_seed", "sn_site_energy",
-    "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_get_boundary",
+    "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_recombination_partial", "sn_recombination_finish", "sn_get_boundary",
     "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak", "sn_philox_kat", "sn_state_hash", "sn_kernel_in_use",
 ]
 
@@ -93,6 +93,8 @@ def load_library() -> C.CDLL:
     lib.sn_potential_map.argtypes = [H, C.c_int, C.c_void_p]
     lib.sn_efield_map.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.sn_recombination.argtypes = [H, C.c_int, C.c_void_p]
+    lib.sn_recombination_partial.argtypes = [H, C.c_int, C.c_void_p]
+    lib.sn_recombination_finish.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     lib.sn_get_boundary.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.sn_set_ghost.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.sn_ipc_export.argtypes = [H, C.c_void_p, C.c_void_p]
@@ -124,6 +126,14 @@ def philox_kat(counter_key, device=False):
     dev = np.zeros((len(ck), 4), np.uint32) if device else None
     _check(load_library().sn_philox_kat(len(ck), ck.ctypes.data, host.ctypes.data, dev.ctypes.data if device else None))
     return host, dev
+
+
+def recombination_finish(parts):
+    """Merge sn_recombination_partial results of the slabs of one lattice (sn_recombination_finish)."""
+    p = np.ascontiguousarray(parts, np.float64).reshape(-1, 9)
+    out = np.zeros(11, np.float64)
+    _check(load_library().sn_recombination_finish(len(p), p.ctypes.data, out.ctypes.data))
+    return out
 
 
 def beta_of_T(T: float) -> float:
@@ -321,6 +331,11 @@ class Simulation:
         v = C.c_int(0)
         _check(self.lib.sn_kernel_in_use(self.h, C.byref(v)))
         return v.value
+
+    def recombination_partial(self, replica=0):
+        v = np.zeros(9, np.float64)
+        _check(self.lib.sn_recombination_partial(self.h, replica, v.ctypes.data))
+        return v
 
     def set_replica_seed(self, seed, replica):
         _check(self.lib.sn_set_replica_seed(self.h, replica, int(seed)))

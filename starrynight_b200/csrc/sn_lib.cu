@@ -814,76 +814,110 @@ extern "C" int sn_landau_order(sn_handle *h, int replica, double *landau)
     return SN_OK;
 }
 
+// Which array holds a replica's sites right now, and where the planes beyond a Z-slab's own live.  Slab neighbours
+// are reached through the array their sweep kernel works on (the pointer sn_ipc_attach / sn_attach_peer stored), so a
+// slab handle is read in that layout too; every slab must be quiescent (same call sequence on all slabs: the next
+// sweep of a neighbour waits for this handle's handshake, which is queued behind the observable kernels).
+static int sn_make_view(sn_handle *h, int replica, int reach, const char *who, SnLatView *v)
+{
+    const SnGeom &G = h->G;
+    int rc;
+    if (!G.periodic_z) {
+        if (!h->peer_lat[0] || !h->peer_lat[1]) return sn_fail(SN_ERR_INVALID, "%s: Z-slab handle has no neighbours attached (sn_ipc_attach / sn_attach_peer)", who);
+        if (G.gz > 0 && G.nz < reach) return sn_fail(SN_ERR_UNSUPPORTED, "%s: slab height %d is smaller than the stencil radius %d", who, G.nz, reach);
+    }
+    if (h->use_tiled && (h->lat2_valid || !G.periodic_z)) {
+        if (!h->lat2_valid) { if ((rc = sn_sync_canonical(h)) || (rc = sn_convert_layout(h, true))) return rc; h->lat2_valid = true; }
+        const long long rs = sn_rep_stride2(G) * replica;
+        v->own = h->lat2 + rs; v->tiled = 1;
+        v->lo = G.periodic_z ? v->own : h->peer_lat[0] + rs;
+        v->hi = G.periodic_z ? v->own : h->peer_lat[1] + rs;
+    } else {
+        if ((rc = sn_sync_canonical(h))) return rc;
+        const long long rs = G.rep_stride * replica;
+        v->own = h->lat + rs; v->tiled = 0;
+        v->lo = G.periodic_z ? v->own : h->peer_lat[0] + rs;
+        v->hi = G.periodic_z ? v->own : h->peer_lat[1] + rs;
+    }
+    return SN_OK;
+}
+
+static int sn_obs_blocks(const sn_handle *h) { return sno::tiles(h->G.X) * sno::tiles(h->G.Y) * sno::tiles(h->G.nz); }
+
 extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum, long long *count)
 {
     SN_CHECK_HANDLE(h, replica);
     if (!fe_sum || !afe_sum || !count) return sn_fail(SN_ERR_INVALID, "sn_rdf: null");
-    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_rdf: not available on a Z-slab handle (radius-9 halo)");
-    const int CUT = 9;                              // analysis.c:540
+    const int CUT = sno::RDF_R;                     // analysis.c:540
+    SnLatView view; int rc = sn_make_view(h, replica, CUT, "sn_rdf", &view);
+    if (rc) return rc;
     std::vector<SnRdfOffset> off;
     std::vector<long long> mult(SN_RDF_BINS, 0);    // lattice vectors per r^2 (both signs): the reference's count per site
-    for (int dx = -CUT; dx <= CUT; dx++) for (int dy = -CUT; dy <= CUT; dy++) for (int dz = -CUT; dz <= CUT; dz++) {
+    const int zc = h->G.gz > 0 ? CUT : CUT;         // the reference walks dz in [-9, 9] whatever Z is (% wraps it)
+    for (int dx = -CUT; dx <= CUT; dx++) for (int dy = -CUT; dy <= CUT; dy++) for (int dz = -zc; dz <= zc; dz++) {
         const int r2 = dx * dx + dy * dy + dz * dz;
         if (r2 >= SN_RDF_BINS) continue;            // r^2 == 81 is neither zeroed nor printed by the reference
         mult[r2]++;
         // one of {d, -d}: the kernel walks the upper half space and the origin, the sums of r^2 > 0 are doubled below
         if (!(dx > 0 || (dx == 0 && dy > 0) || (dx == 0 && dy == 0 && dz >= 0))) continue;
-        SnRdfOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.r2 = (short)r2;
+        SnRdfOffset o;
+        o.delta = (dx * sno::RDF_NY + dy) * sno::RDF_NZ + dz; o.r2 = r2;
+        o.dx = dx; o.dy = dy; o.dz = dz; o.k = r2 > 0 ? 3.0 / (double)r2 : 0.0;
         off.push_back(o);
     }
     std::stable_sort(off.begin(), off.end(), [](const SnRdfOffset &a, const SnRdfOffset &b) { return a.r2 < b.r2; });
     std::vector<int> first(SN_RDF_BINS + 1, 0);
     for (auto &o : off) first[o.r2 + 1]++;
     for (int b = 0; b < SN_RDF_BINS; b++) first[b + 1] += first[b];
-    const bool near = h->G.X >= CUT && h->G.Y >= CUT && h->G.nz >= CUT;
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
-    const int nblocks = (int)((n + 255) / 256);
-    const size_t b_off = off.size() * sizeof(SnRdfOffset), b_first = first.size() * sizeof(int);
-    const size_t b_out = sizeof(double) * 2 * SN_RDF_BINS * (size_t)nblocks;
-    void *s; int rc = sn_scratch(h, b_out + b_off + b_first + 256, &s);
-    if (rc || (rc = sn_sync_canonical(h))) return rc;
-    double *d_out = (double *)s;
-    SnRdfOffset *d_off = (SnRdfOffset *)((char *)s + b_out);
-    int *d_first = (int *)((char *)s + b_out + ((b_off + 15) / 16) * 16);
-    SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));
+    const int nblocks = sn_obs_blocks(h), nv = 2 * SN_RDF_BINS;
+    const size_t b_part = sizeof(double) * nv * (size_t)nblocks, b_tot = sizeof(double) * nv;
+    const size_t b_off = ((off.size() * sizeof(SnRdfOffset) + 15) / 16) * 16, b_first = first.size() * sizeof(int);
+    void *s; if ((rc = sn_scratch(h, b_part + b_tot + b_off + b_first + 256, &s))) return rc;
+    double *d_part = (double *)s, *d_tot = d_part + (size_t)nv * nblocks;
+    SnRdfOffset *d_off = (SnRdfOffset *)((char *)s + b_part + b_tot);
+    int *d_first = (int *)((char *)d_off + b_off);
+    SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(SnRdfOffset), cudaMemcpyHostToDevice, h->stream));
     SN_CUDA_CHECK(cudaMemcpyAsync(d_first, first.data(), b_first, cudaMemcpyHostToDevice, h->stream));
-    if (near) sn_rdf_kernel<true><<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, d_first, SN_RDF_BINS, d_out);
-    else sn_rdf_kernel<false><<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, d_first, SN_RDF_BINS, d_out);
+    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_rdf_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sno::RDF_SMEM));
+    sn_rdf_tiled_kernel<<<nblocks, sno::THREADS, sno::RDF_SMEM, h->stream>>>(view, h->G, d_off, d_first, SN_RDF_BINS, d_part);
+    sn_reduce_rows_kernel<<<nv, 256, 0, h->stream>>>(d_part, nblocks, nv, d_tot);
     SN_CUDA_CHECK(cudaGetLastError());
-    std::vector<double> tot(2 * SN_RDF_BINS);
-    if ((rc = sn_reduce_to_host(h, d_out, nblocks, 2 * SN_RDF_BINS, tot.data()))) return rc;
+    std::vector<double> tot(nv);
+    SN_CUDA_CHECK(cudaMemcpyAsync(tot.data(), d_tot, b_tot, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     for (int b = 0; b < SN_RDF_BINS; b++) {
         const double twice = b == 0 ? 1.0 : 2.0;
         fe_sum[b] = twice * tot[2 * b]; afe_sum[b] = twice * tot[2 * b + 1];
         count[b] = mult[b] * n;                                     // analysis.c:578, one count per (site, offset)
     }
-    return SN_OK;
+    return sn_check_device_error(h);
 }
 
-// potential map into device scratch (first n doubles of *scratch); extra_bytes are reserved behind it
+// potential map of the handle's own sites into device scratch (first n doubles of *scratch); extra_bytes are reserved behind it
 static int sn_potential_device(sn_handle *h, int replica, size_t extra_bytes, double **d_v, void **extra)
 {
-    const int MAXR = 6;                             // analysis.c:68
+    const int MAXR = sno::POT_R;                    // analysis.c:68
+    SnLatView view; int rc = sn_make_view(h, replica, MAXR, "sn_potential_map", &view);
+    if (rc) return rc;
     std::vector<SnPotOffset> off;
     for (int dx = -MAXR; dx <= MAXR; dx++) for (int dy = -MAXR; dy <= MAXR; dy++) for (int dz = -MAXR; dz <= MAXR; dz++) {
         if (!dx && !dy && !dz) continue;
         const double d = sqrt((double)(dx * dx + dy * dy + dz * dz));
         if (d > (double)MAXR) continue;
-        SnPotOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.pad = 0; o.w = 1.0 / (d * d * d);
+        const double w = 1.0 / (d * d * d);
+        SnPotOffset o; o.delta = (dx * sno::POT_N + dy) * sno::POT_N + dz; o.pad = 0; o.kx = dx * w; o.ky = dy * w; o.kz = dz * w;
         off.push_back(o);
     }
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     const size_t b_v = ((sizeof(double) * n + 15) / 16) * 16, b_off = ((off.size() * sizeof(SnPotOffset) + 15) / 16) * 16;
-    void *s; int rc = sn_scratch(h, b_v + b_off + extra_bytes + 64, &s);
-    if (rc || (rc = sn_sync_canonical(h))) return rc;
+    void *s; if ((rc = sn_scratch(h, b_v + b_off + extra_bytes + 64, &s))) return rc;
     *d_v = (double *)s;
     SnPotOffset *d_off = (SnPotOffset *)((char *)s + b_v);
     if (extra) *extra = (char *)s + b_v + b_off;
     SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(SnPotOffset), cudaMemcpyHostToDevice, h->stream));
-    if (h->G.X >= MAXR && h->G.Y >= MAXR && h->G.nz >= MAXR)
-        sn_potential_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), *d_v);
-    else
-        sn_potential_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(), *d_v);
+    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_potential_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sno::POT_SMEM));
+    sn_potential_tiled_kernel<<<sn_obs_blocks(h), sno::THREADS, sno::POT_SMEM, h->stream>>>(view, h->G, d_off, (int)off.size(), *d_v);
     SN_CUDA_CHECK(cudaGetLastError());
     return SN_OK;
 }
@@ -892,13 +926,12 @@ extern "C" int sn_potential_map(sn_handle *h, int replica, double *V)
 {
     SN_CHECK_HANDLE(h, replica);
     if (!V) return sn_fail(SN_ERR_INVALID, "sn_potential_map: null");
-    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_potential_map: not available on a Z-slab handle (radius-6 halo)");
     double *d_v; int rc = sn_potential_device(h, replica, 0, &d_v, nullptr);
     if (rc) return rc;
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     SN_CUDA_CHECK(cudaMemcpyAsync(V, d_v, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    return SN_OK;
+    return sn_check_device_error(h);
 }
 
 extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_offset, double *Emag)
@@ -906,11 +939,14 @@ extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_off
     SN_CHECK_HANDLE(h, replica);
     if (!Emag) return sn_fail(SN_ERR_INVALID, "sn_efield_map: null");
     if (cutoff < 1 || cutoff > 8) return sn_fail(SN_ERR_INVALID, "sn_efield_map: cutoff %d outside 1..8", cutoff);
-    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_efield_map: not available on a Z-slab handle (halo wider than the ghost shell)");
     // offsets as the reference walks them: integer steps without the origin (analysis.c:407-418), or
     // dx + 0.5 for dx in [-cutoff-1, cutoff-1] (analysis.c:322-334); d <= cutoff
     const int lo = half_offset ? -cutoff - 1 : -cutoff, hi = half_offset ? cutoff - 1 : cutoff;
-    std::vector<SnEfOffset> off;
+    const int reach = cutoff + (half_offset ? 1 : 0);
+    const bool tiled = reach <= 6;                  // the box of an 8^3 tile with a halo of 6 fits in shared memory
+    if (!tiled && !h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_efield_map: cutoff %d on a Z-slab handle (radius above 6)", cutoff);
+    const int N = sno::T + 2 * reach;
+    std::vector<SnEfOffset> off; std::vector<SnEfOffset2> off2;
     for (int dx = lo; dx <= hi; dx++) for (int dy = lo; dy <= hi; dy++) for (int dz = lo; dz <= hi; dz++) {
         if (!half_offset && !dx && !dy && !dz) continue;
         const double sh = half_offset ? 0.5 : 0.0, rx = dx + sh, ry = dy + sh, rz = dz + sh;
@@ -919,24 +955,80 @@ extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_off
         SnEfOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.pad = 0;
         o.nx = rx / d; o.ny = ry / d; o.nz = rz / d; o.w = 1.0 / (d * d * d);
         off.push_back(o);
+        SnEfOffset2 q; q.delta = (dx * N + dy) * N + dz; q.pad = 0; q.nx = o.nx; q.ny = o.ny; q.nz = o.nz; q.w = o.w;
+        off2.push_back(q);
     }
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
-    const size_t b_v = ((sizeof(double) * n + 15) / 16) * 16, b_off = off.size() * sizeof(SnEfOffset);
+    const size_t b_v = ((sizeof(double) * n + 15) / 16) * 16, b_off = off.size() * std::max(sizeof(SnEfOffset), sizeof(SnEfOffset2));
     void *s; int rc = sn_scratch(h, b_v + b_off + 64, &s);
-    if (rc || (rc = sn_sync_canonical(h))) return rc;
+    if (rc) return rc;
     double *d_v = (double *)s;
-    SnEfOffset *d_off = (SnEfOffset *)((char *)s + b_v);
-    SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), b_off, cudaMemcpyHostToDevice, h->stream));
-    const int reach = cutoff + 1;                   // the half-offset variant walks dx down to -cutoff-1
-    if (h->G.X >= reach && h->G.Y >= reach && h->G.nz >= reach)
-        sn_efield_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(),
-                                                                                    half_offset ? 0 : 1, d_v);
-    else
-        sn_efield_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->lat + (long long)replica * h->G.rep_stride, h->G, d_off, (int)off.size(),
-                                                                                     half_offset ? 0 : 1, d_v);
+    void *d_off = (char *)s + b_v;
+    if (tiled) {
+        SnLatView view;
+        if ((rc = sn_make_view(h, replica, reach, "sn_efield_map", &view))) return rc;
+        const int smem = N * N * N * 24;
+        SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off2.data(), off2.size() * sizeof(SnEfOffset2), cudaMemcpyHostToDevice, h->stream));
+        SN_CUDA_CHECK(cudaFuncSetAttribute(sn_efield_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sno::POT_SMEM));
+        sn_efield_tiled_kernel<<<sn_obs_blocks(h), sno::THREADS, smem, h->stream>>>(view, h->G, (const SnEfOffset2 *)d_off, (int)off2.size(), reach,
+                                                                                      half_offset ? 0 : 1, d_v);
+    } else {
+        if ((rc = sn_sync_canonical(h))) return rc;
+        SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(SnEfOffset), cudaMemcpyHostToDevice, h->stream));
+        const float4 *lat = h->lat + (long long)replica * h->G.rep_stride;
+        if (h->G.X >= reach && h->G.Y >= reach && h->G.nz >= reach)
+            sn_efield_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(lat, h->G, (const SnEfOffset *)d_off, (int)off.size(), half_offset ? 0 : 1, d_v);
+        else
+            sn_efield_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(lat, h->G, (const SnEfOffset *)d_off, (int)off.size(), half_offset ? 0 : 1, d_v);
+    }
     SN_CUDA_CHECK(cudaGetLastError());
     SN_CUDA_CHECK(cudaMemcpyAsync(Emag, d_v, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    return sn_check_device_error(h);
+}
+
+// recombination_calculator() (analysis.c:96-170) in two halves, so that the slabs of a decomposed lattice can be merged:
+// partial sums over the handle's own sites, then the normalisations over the whole lattice.
+extern "C" int sn_recombination_partial(sn_handle *h, int replica, double part[SN_RECOMB_PARTIAL_N])
+{
+    SN_CHECK_HANDLE(h, replica);
+    if (!part) return sn_fail(SN_ERR_INVALID, "sn_recombination_partial: null");
+    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
+    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
+    double *d_v; void *extra;
+    int rc = sn_potential_device(h, replica, sizeof(double) * 8 * nblocks, &d_v, &extra);
+    if (rc) return rc;
+    const double BETA = 1 / (0.025), potentialeV = 0.165 / 5;                 // analysis.c:104-106
+    sn_recombination_kernel<<<nblocks, 256, 0, h->stream>>>(d_v, n, h->G.nz, h->G.z0 == 0 ? 1 : 0, potentialeV * BETA, (double *)extra);
+    SN_CUDA_CHECK(cudaGetLastError());
+    std::vector<double> hp((size_t)nblocks * 8);
+    SN_CUDA_CHECK(cudaMemcpyAsync(hp.data(), extra, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < SN_RECOMB_PARTIAL_N; k++) part[k] = 0.0;
+    for (int b = 0; b < nblocks; b++) {
+        for (int k = 0; k < 5; k++) part[k] += hp[(size_t)b * 8 + k];
+        for (int k = 5; k < 8; k++) part[k] = std::max(part[k], hp[(size_t)b * 8 + k]);
+    }
+    part[8] = (double)n;
+    return sn_check_device_error(h);
+}
+
+extern "C" int sn_recombination_finish(int nparts, const double *parts, double out[SN_RECOMB_N])
+{
+    if (nparts < 1 || !parts || !out) return sn_fail(SN_ERR_INVALID, "sn_recombination_finish: bad arguments");
+    double sum[5] = {0, 0, 0, 0, 0}, mx[3] = {0, 0, 0}, N = 0.0;
+    for (int p = 0; p < nparts; p++) {
+        const double *q = parts + (size_t)p * SN_RECOMB_PARTIAL_N;
+        for (int k = 0; k < 5; k++) sum[k] += q[k];
+        for (int k = 0; k < 3; k++) mx[k] = std::max(mx[k], q[5 + k]);
+        N += q[8];
+    }
+    const double ZBe = sum[0], ZBh = sum[1], ZFDe = sum[2], ZFDh = sum[3];
+    out[0] = ZBe; out[1] = ZBh; out[2] = ZFDe; out[3] = ZFDh;
+    out[4] = N * N / (ZBe * ZBh);                                             // R_Boltz (:131; in double, the reference's int product wraps)
+    out[5] = N * sum[4] / (ZFDe * ZFDh);                                      // R_FD = N * sum e_i h_i (:169)
+    out[6] = sum[2] / ZFDe; out[7] = sum[3] / ZFDh;                            // FD totals (:163-164)
+    out[8] = mx[0] / ZFDe; out[9] = mx[1] / ZFDh; out[10] = mx[2] / (ZFDe * ZFDh);   // maxima over z = 0 (:157-159)
     return SN_OK;
 }
 
@@ -944,30 +1036,12 @@ extern "C" int sn_recombination(sn_handle *h, int replica, double out[SN_RECOMB_
 {
     SN_CHECK_HANDLE(h, replica);
     if (!out) return sn_fail(SN_ERR_INVALID, "sn_recombination: null");
-    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_recombination: not available on a Z-slab handle (radius-6 halo)");
-    const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
-    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
-    double *d_v; void *extra;
-    int rc = sn_potential_device(h, replica, sizeof(double) * 8 * nblocks, &d_v, &extra);
+    if (!h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_recombination: a Z-slab handle holds part of the lattice: merge the slabs' "
+                                                             "sn_recombination_partial results with sn_recombination_finish");
+    double part[SN_RECOMB_PARTIAL_N];
+    int rc = sn_recombination_partial(h, replica, part);
     if (rc) return rc;
-    const double BETA = 1 / (0.025), potentialeV = 0.165 / 5;                 // analysis.c:104-106
-    sn_recombination_kernel<<<nblocks, 256, 0, h->stream>>>(d_v, n, h->G.nz, potentialeV * BETA, (double *)extra);
-    SN_CUDA_CHECK(cudaGetLastError());
-    std::vector<double> hp((size_t)nblocks * 8);
-    SN_CUDA_CHECK(cudaMemcpyAsync(hp.data(), extra, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    double sum[5] = {0, 0, 0, 0, 0}, mx[3] = {0, 0, 0};
-    for (int b = 0; b < nblocks; b++) {
-        for (int k = 0; k < 5; k++) sum[k] += hp[(size_t)b * 8 + k];
-        for (int k = 0; k < 3; k++) mx[k] = std::max(mx[k], hp[(size_t)b * 8 + 5 + k]);
-    }
-    const double ZBe = sum[0], ZBh = sum[1], ZFDe = sum[2], ZFDh = sum[3], N = (double)n;
-    out[0] = ZBe; out[1] = ZBh; out[2] = ZFDe; out[3] = ZFDh;
-    out[4] = N * N / (ZBe * ZBh);                                             // R_Boltz (:131; in double, the reference's int product wraps)
-    out[5] = N * sum[4] / (ZFDe * ZFDh);                                      // R_FD = N * sum e_i h_i (:169)
-    out[6] = sum[2] / ZFDe; out[7] = sum[3] / ZFDh;                            // FD totals (:163-164)
-    out[8] = mx[0] / ZFDe; out[9] = mx[1] / ZFDh; out[10] = mx[2] / (ZFDe * ZFDh);   // maxima over z = 0 (:157-159)
-    return SN_OK;
+    return sn_recombination_finish(1, part, out);
 }
 
 // ---- Philox known-answer check ---------------------------------------------------
@@ -1074,7 +1148,7 @@ static int sn_preload_kernels(int device)
         (const void *)sn_sum_dipoles_kernel, (const void *)sn_state_hash_kernel, (const void *)sn_sum_doubles_kernel,
         (const void *)sn_energy_f32_kernel<0, true>, (const void *)sn_energy_f32_kernel<1, true>, (const void *)sn_energy_f32_kernel<2, true>,
         (const void *)sn_site_energy_f32_kernel<0, true>, (const void *)sn_site_energy_f32_kernel<1, true>, (const void *)sn_site_energy_f32_kernel<2, true>,
-        (const void *)sn_rdf_kernel<true>, (const void *)sn_rdf_kernel<false>, (const void *)sn_potential_kernel<true>, (const void *)sn_potential_kernel<false>,
+        (const void *)sn_rdf_tiled_kernel, (const void *)sn_potential_tiled_kernel, (const void *)sn_efield_tiled_kernel, (const void *)sn_reduce_rows_kernel,
         (const void *)sn_efield_kernel<true>, (const void *)sn_efield_kernel<false>, (const void *)sn_recombination_kernel,
     };
     for (const void *k : kernels) {

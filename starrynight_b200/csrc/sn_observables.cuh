@@ -161,68 +161,190 @@ __global__ void __launch_bounds__(128) sn_site_energy_f32_kernel(const float4 *_
     out[i] = (double)sn_delta_e(old, make_float3(newdip[3 * i], newdip[3 * i + 1], newdip[3 * i + 2]), F, Gc, t);
 }
 
-// ---- radial order parameter (analysis.c:528-598) ------------------------------
-// Offsets inside the radius-9 sphere are sorted by r^2 on the host; `first[b]`
-// is the first offset of bin b.  Only one of every pair {d, -d} is walked: on a periodic lattice the
-// pairs (i, i+d) over all sites i are the pairs (j-d, j) over all j, and both correlations are symmetric
-// in their two dipoles, so the host doubles the sums of r^2 > 0 (half the 3071 pair terms per site).  Each thread walks every offset for its site,
-// keeps the running FE / AFE sums of the current bin in registers, and the block
-// reduces them once per bin -> out[block][bin][2].
-struct SnRdfOffset { short dx, dy, dz, r2; };
+// ---- shared-memory-tiled stencils ------------------------------------------------------------------
+// RDF (radius 9), potential (radius 6) and E-field (radius <= 6) walk hundreds to thousands of neighbours per site.
+// A CTA owns an 8^3 block of sites, stages the block plus its halo in shared memory once (every site of the box is
+// then read ~500-1500 times from there instead of through L1/L2), and each thread walks the offset list for 2 sites.
+// The loader resolves the periodic wrap (any extent, also smaller than the radius: images repeat, as the
+// reference's % arithmetic does) and, for a Z-slab handle, reads planes beyond its own from the neighbouring
+// GPUs' lattices over NVLink -- the observables of a decomposed lattice need no gather.
 
-template <bool NEAR>
-__global__ void __launch_bounds__(256) sn_rdf_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnRdfOffset *__restrict__ off,
-                                                     const int *__restrict__ first, int nbins, double *__restrict__ out)
+// Where a replica's sites live: the handle's own array, the slab neighbours' (same geometry), in the canonical
+// padded layout or the tiled kernel's de-interleaved one.
+struct SnLatView {
+    const float4 *own, *lo, *hi;        // replica bases; lo / hi = own for a handle that owns the whole Z axis
+    int tiled;
+};
+
+__device__ __forceinline__ float4 sn_view_site(const SnLatView &v, const SnGeom &G, int x, int y, int z)
 {
+    const float4 *b = v.own;            // x, y already wrapped into the lattice; z in [-nz, 2 nz)
+    if (z < 0) { b = v.lo; z += G.nz; } else if (z >= G.nz) { b = v.hi; z -= G.nz; }
+    return v.tiled ? b[sn_pidx2(G, x, y, z)] : b[sn_pidx(G, x, y, z)];
+}
+
+namespace sno {
+constexpr int T = 8;                     // tile edge
+constexpr int THREADS = 256;             // each thread: sites t and t + 256 of the tile (x and x + 4)
+__host__ __device__ inline int tiles(int n) { return (n + T - 1) / T; }
+__device__ __forceinline__ int wrap(int v, int n) { v %= n; return v < 0 ? v + n : v; }
+}
+
+// box cell i -> lattice site; calls put(i, float4)
+template <class Put>
+__device__ __forceinline__ void sn_load_box(const SnLatView &view, const SnGeom &G, int bx0, int by0, int bz0, int nx, int ny, int nzb, Put &&put)
+{
+    const int cells = nx * ny * nzb;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        const int lz = i % nzb, ly = (i / nzb) % ny, lx = i / (nzb * ny);
+        const int x = sno::wrap(bx0 + lx, G.X), y = sno::wrap(by0 + ly, G.Y);
+        int z = bz0 + lz;
+        if (G.periodic_z) z = sno::wrap(z, G.nz);
+        put(i, sn_view_site(view, G, x, y, z));
+    }
+}
+
+__device__ __forceinline__ void sn_tile_origin(const SnGeom &G, int &x0, int &y0, int &z0)
+{
+    const int tz = sno::tiles(G.nz), ty = sno::tiles(G.Y);
+    const int b = blockIdx.x;
+    z0 = (b % tz) * sno::T; y0 = ((b / tz) % ty) * sno::T; x0 = (b / (tz * ty)) * sno::T;
+}
+
+// sum of nrows rows of nv doubles, one block per column, fixed order: bit-reproducible
+__global__ void __launch_bounds__(256) sn_reduce_rows_kernel(const double *__restrict__ in, long long nrows, int nv, double *__restrict__ out)
+{
+    __shared__ double sm[8];
+    double v[1] = {0.0};
+    for (long long r = threadIdx.x; r < nrows; r += 256) v[0] += in[r * nv + blockIdx.x];
+    sn_block_sum<1, 256>(v, sm);
+    if (threadIdx.x == 0) out[blockIdx.x] = v[0];
+}
+
+// ---- radial order parameter (analysis.c:528-598) ------------------------------
+// Offsets inside the radius-9 sphere are sorted by r^2 on the host; `first[b]` is the first offset of bin b.  Only
+// one of every pair {d, -d} is walked: on a periodic lattice the pairs (i, i+d) over all sites i are the pairs
+// (j-d, j) over all j, and both correlations are symmetric in their two dipoles, so the host doubles the sums of
+// r^2 > 0 (half the 3071 pair terms per site).  The half space walked is dx > 0, or dx = 0 and dy > 0, or
+// dx = dy = 0 and dz >= 0, so the box is 17 x 26 x 26 sites (184 KB as float4).  FP64 throughout, block-reduced
+// once per bin -> out[block][bin][2]; sn_reduce_rows_kernel adds the blocks.
+struct SnRdfOffset { int delta; int r2; double dx, dy, dz, k; };     // delta: box index step; k = 3 / r^2 (0 at the origin)
+namespace sno { constexpr int RDF_R = 9, RDF_NX = T + RDF_R, RDF_NY = T + 2 * RDF_R, RDF_NZ = T + 2 * RDF_R;
+                constexpr int RDF_SMEM = RDF_NX * RDF_NY * RDF_NZ * 16; }
+
+__global__ void __launch_bounds__(sno::THREADS, 1) sn_rdf_tiled_kernel(const SnLatView view, const SnGeom G, const SnRdfOffset *__restrict__ off,
+                                                                       const int *__restrict__ first, int nbins, double *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char sn_obs_smem[];
+    float4 *box = reinterpret_cast<float4 *>(sn_obs_smem);
     __shared__ double sm[2 * 8];
-    const long long n = (long long)G.X * G.Y * G.nz;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    int x = 0, y = 0, z = 0;
-    if (live) sn_site_of(G, i, x, y, z);
-    const float4 a = live ? lat[sn_pidx(G, x, y, z)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int x0, y0, z0; sn_tile_origin(G, x0, y0, z0);
+    sn_load_box(view, G, x0, y0 - sno::RDF_R, z0 - sno::RDF_R, sno::RDF_NX, sno::RDF_NY, sno::RDF_NZ, [&](int i, float4 v) { box[i] = v; });
+    __syncthreads();
+    int base[2]; bool live[2]; double ax[2], ay[2], az[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
+        live[s] = x0 + lx < G.X && y0 + ly < G.Y && z0 + lz < G.nz;
+        base[s] = (lx * sno::RDF_NY + ly + sno::RDF_R) * sno::RDF_NZ + lz + sno::RDF_R;
+        const float4 a = box[base[s]];
+        ax[s] = live[s] ? (double)a.x : 0.0; ay[s] = live[s] ? (double)a.y : 0.0; az[s] = live[s] ? (double)a.z : 0.0;   // a dead site adds exact zeros
+    }
     for (int b = 0; b < nbins; b++) {
+        const int o0 = first[b], o1 = first[b + 1];
         double v[2] = {0.0, 0.0};
-        const int e = first[b + 1];
-        for (int o = first[b]; o < e && live; o++) {
+        for (int o = o0; o < o1; o++) {
             const SnRdfOffset f = off[o];
-            const int xx = sn_wrap<NEAR>(x + f.dx, G.X), yy = sn_wrap<NEAR>(y + f.dy, G.Y), zz = sn_wrap<NEAR>(z + f.dz, G.nz);
-            const float4 c = lat[sn_pidx(G, xx, yy, zz)];
-            const double fe = (double)a.x * c.x + (double)a.y * c.y + (double)a.z * c.z;
-            double afe = fe;
-            if (f.r2 > 0) {
-                const double na = (double)f.dx * a.x + (double)f.dy * a.y + (double)f.dz * a.z;
-                const double nc = (double)f.dx * c.x + (double)f.dy * c.y + (double)f.dz * c.z;
-                afe = fe - 3.0 * na * nc / (double)f.r2;
-            } else afe = fe - 3.0 * 0.0;       // d forced to 1, n = 0 (analysis.c:571-573)
-            v[0] += fe; v[1] += afe;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const float4 c = box[base[s] + f.delta];
+                const double cx = c.x, cy = c.y, cz = c.z;
+                const double fe = ax[s] * cx + ay[s] * cy + az[s] * cz;
+                const double na = f.dx * ax[s] + f.dy * ay[s] + f.dz * az[s];
+                const double nc = f.dx * cx + f.dy * cy + f.dz * cz;
+                v[0] += fe;
+                v[1] += fe - f.k * na * nc;                 // fe - 3 (n.a)(n.c), n = d / |d| (analysis.c:574-576); k = 0 at the origin (:571-573)
+            }
         }
-        if (e > first[b]) {                    // uniform across the block
-            sn_block_sum<2, 256>(v, sm);
-            if (threadIdx.x == 0) { out[((long long)blockIdx.x * nbins + b) * 2] = v[0]; out[((long long)blockIdx.x * nbins + b) * 2 + 1] = v[1]; }
-        } else if (threadIdx.x == 0) { out[((long long)blockIdx.x * nbins + b) * 2] = 0.0; out[((long long)blockIdx.x * nbins + b) * 2 + 1] = 0.0; }
+        if (o1 > o0) sn_block_sum<2, sno::THREADS>(v, sm);      // uniform across the block
+        if (threadIdx.x == 0) { out[((long long)blockIdx.x * nbins + b) * 2] = v[0]; out[((long long)blockIdx.x * nbins + b) * 2 + 1] = v[1]; }
     }
 }
 
 // ---- electrostatic potential map (analysis.c:65-94) ---------------------------
-struct SnPotOffset { short dx, dy, dz, pad; double w; };   // w = 1/d^3
+// V_i = sum_{0 < d <= 6} l_j (p_j . r) / d^3.  The box holds the moments m_j = l_j p_j as doubles (the product of two
+// floats is exact in double), component-wise arrays so that consecutive lanes read consecutive words; the offset
+// table holds r / d^3.  3 FMA and 3 shared-memory loads per pair term.
+struct SnPotOffset { int delta; int pad; double kx, ky, kz; };
+namespace sno { constexpr int POT_R = 6, POT_N = T + 2 * POT_R, POT_CELLS = POT_N * POT_N * POT_N, POT_SMEM = POT_CELLS * 24; }
 
-template <bool NEAR>
-__global__ void __launch_bounds__(128) sn_potential_kernel(const float4 *__restrict__ lat, const SnGeom G, const SnPotOffset *__restrict__ off,
-                                                           int noff, double *__restrict__ V)
+__global__ void __launch_bounds__(sno::THREADS, 1) sn_potential_tiled_kernel(const SnLatView view, const SnGeom G, const SnPotOffset *__restrict__ off,
+                                                                             int noff, double *__restrict__ V)
 {
-    const long long n = (long long)G.X * G.Y * G.nz;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int x, y, z; sn_site_of(G, i, x, y, z);
-    double pot = 0.0;
+    extern __shared__ __align__(16) unsigned char sn_obs_smem[];
+    double *mx = reinterpret_cast<double *>(sn_obs_smem), *my = mx + sno::POT_CELLS, *mz = my + sno::POT_CELLS;
+    int x0, y0, z0; sn_tile_origin(G, x0, y0, z0);
+    sn_load_box(view, G, x0 - sno::POT_R, y0 - sno::POT_R, z0 - sno::POT_R, sno::POT_N, sno::POT_N, sno::POT_N,
+                [&](int i, float4 v) { mx[i] = (double)v.w * v.x; my[i] = (double)v.w * v.y; mz[i] = (double)v.w * v.z; });
+    __syncthreads();
+    int base[2]; double pot[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
+        base[s] = ((lx + sno::POT_R) * sno::POT_N + ly + sno::POT_R) * sno::POT_N + lz + sno::POT_R;
+    }
     for (int o = 0; o < noff; o++) {
         const SnPotOffset f = off[o];
-        const int xx = sn_wrap<NEAR>(x + f.dx, G.X), yy = sn_wrap<NEAR>(y + f.dy, G.Y), zz = sn_wrap<NEAR>(z + f.dz, G.nz);
-        const float4 c = lat[sn_pidx(G, xx, yy, zz)];
-        pot += (double)c.w * ((double)c.x * f.dx + (double)c.y * f.dy + (double)c.z * f.dz) * f.w;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int c = base[s] + f.delta;
+            pot[s] += mx[c] * f.kx + my[c] * f.ky + mz[c] * f.kz;
+        }
     }
-    V[i] = pot;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
+        if (x0 + lx < G.X && y0 + ly < G.Y && z0 + lz < G.nz) V[((long long)(x0 + lx) * G.Y + y0 + ly) * G.nz + z0 + lz] = pot[s];
+    }
+}
+
+// ---- dipole electric-field maps, tiled (analysis.c:310-376, 393-465); reach <= 6 --------------------
+struct SnEfOffset2 { int delta; int pad; double nx, ny, nz, w; };    // n = r / d, w = 1 / d^3
+
+__global__ void __launch_bounds__(sno::THREADS, 1) sn_efield_tiled_kernel(const SnLatView view, const SnGeom G, const SnEfOffset2 *__restrict__ off,
+                                                                          int noff, int reach, int self_term, double *__restrict__ Emag)
+{
+    extern __shared__ __align__(16) unsigned char sn_obs_smem[];
+    const int N = sno::T + 2 * reach, cells = N * N * N;
+    double *px = reinterpret_cast<double *>(sn_obs_smem), *py = px + cells, *pz = py + cells;
+    int x0, y0, z0; sn_tile_origin(G, x0, y0, z0);
+    sn_load_box(view, G, x0 - reach, y0 - reach, z0 - reach, N, N, N, [&](int i, float4 v) { px[i] = v.x; py[i] = v.y; pz[i] = v.z; });
+    __syncthreads();
+    int base[2]; double ex[2] = {0.0, 0.0}, ey[2] = {0.0, 0.0}, ez[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
+        base[s] = ((lx + reach) * N + ly + reach) * N + lz + reach;
+    }
+    for (int o = 0; o < noff; o++) {
+        const SnEfOffset2 f = off[o];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int c = base[s] + f.delta;
+            const double cx = px[c], cy = py[c], cz = pz[c];
+            const double radial = f.nx * cx + f.ny * cy + f.nz * cz;          // species length not applied (analysis.c:429-434)
+            ex[s] += (3.0 * f.nx * radial - cx) * f.w;
+            ey[s] += (3.0 * f.ny * radial - cy) * f.w;
+            ez[s] += (3.0 * f.nz * radial - cz) * f.w;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
+        if (!(x0 + lx < G.X && y0 + ly < G.Y && z0 + lz < G.nz)) continue;
+        if (self_term) { ex[s] -= px[base[s]] / 3.0; ey[s] -= py[base[s]] / 3.0; ez[s] -= pz[base[s]] / 3.0; }   // analysis.c:457-459
+        Emag[((long long)(x0 + lx) * G.Y + y0 + ly) * G.nz + z0 + lz] = sqrt(ex[s] * ex[s] + ey[s] * ey[s] + ez[s] * ez[s]);
+    }
 }
 
 // ---- dipole electric-field maps (analysis.c:310-376, 393-465) -------------------
@@ -257,7 +379,7 @@ __global__ void __launch_bounds__(128) sn_efield_kernel(const float4 *__restrict
 // One pass over the potential map: partial sums of exp(-bV), exp(bV), f_e = 1/(exp(bV)+1), f_h = 1/(exp(-bV)+1)
 // and f_e f_h, and the maxima of f_e, f_h, f_e f_h over the z = 0 plane -> out[block][8].  The
 // normalisations by Z_FDe, Z_FDh are applied on the host.
-__global__ void __launch_bounds__(256) sn_recombination_kernel(const double *__restrict__ V, long long n, int nz, double scale,
+__global__ void __launch_bounds__(256) sn_recombination_kernel(const double *__restrict__ V, long long n, int nz, int has_z0, double scale,
                                                                double *__restrict__ out)
 {
     __shared__ double sm[5 * 8];
@@ -268,7 +390,7 @@ __global__ void __launch_bounds__(256) sn_recombination_kernel(const double *__r
         const double ep = exp(a), em = exp(-a);
         const double fe = 1.0 / (ep + 1.0), fh = 1.0 / (em + 1.0);
         v[0] += em; v[1] += ep; v[2] += fe; v[3] += fh; v[4] += fe * fh;
-        if (i % nz == 0) { m[0] = fmax(m[0], fe); m[1] = fmax(m[1], fh); m[2] = fmax(m[2], fe * fh); }
+        if (has_z0 && i % nz == 0) { m[0] = fmax(m[0], fe); m[1] = fmax(m[1], fh); m[2] = fmax(m[2], fe * fh); }
     }
     sn_block_sum<5, 256>(v, sm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
