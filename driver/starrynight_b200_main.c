@@ -249,10 +249,13 @@ static double *Vbuf;
 static float *latbuf;
 static int cur = 0;                       /* replica the analysis routines look at (temperature batches) */
 
-/* ---- the sweep engine: one handle, or GPUs slab handles + a full-lattice analysis handle ---- */
+/* ---- the sweep engine: one handle, or one Z-slab handle per GPU ----------------------------------
+ * With GPUs > 1 there is no full-lattice handle: the slabs sweep, and the analysis routines run on the slabs
+ * themselves (each over its own sites, planes beyond the slab read from the neighbouring GPUs), merged here. */
 static sn_handle *slab[16];
 static float *slabbuf;
-static int analysis_stale = 0;
+static double *slabV;
+static int slabs_tiled = 1;
 
 static void slab_planes(const float *lat, float *dst, int zfirst, int nplanes)   /* planes zfirst.. (periodic) of lat[X][Y][Z][4] */
 {
@@ -263,35 +266,41 @@ static void slab_planes(const float *lat, float *dst, int zfirst, int nplanes)  
 
 static void slabs_create(const sn_params *base, const float *lat)
 {
-    int r; const int nz = Z / ngpus, g = DipoleCutOff;
-    float *ghost = (float *)malloc((size_t)X * Y * g * 4 * sizeof(float));
+    int r, k, ndev = 0; const int nz = Z / ngpus;
+    SN(sn_device_count(&ndev));
+    if (ndev < 1) { fprintf(stderr, "no CUDA device\n"); exit(EXIT_FAILURE); }
+    if (device + ngpus > ndev) fprintf(stderr, "GPUs = %d but %d device(s) visible: several slabs share a device (they split its SMs)\n", ngpus, ndev);
     slabbuf = (float *)malloc((size_t)X * Y * nz * 4 * sizeof(float));
-    if (Z % ngpus || !ghost || !slabbuf) { fprintf(stderr, "GPUs = %d does not divide Z = %d\n", ngpus, Z); exit(EXIT_FAILURE); }
+    slabV = (double *)malloc((size_t)X * Y * nz * sizeof(double));
+    if (Z % ngpus || !slabbuf || !slabV) { fprintf(stderr, "GPUs = %d does not divide Z = %d\n", ngpus, Z); exit(EXIT_FAILURE); }
     for (r = 0; r < ngpus; r++) {
         sn_params p = *base;
-        p.device = device + r; p.z0 = r * nz; p.nz = nz;
+        p.device = (device + r) % ndev; p.z0 = r * nz; p.nz = nz;
         SN(sn_create(&p, &slab[r]));
         slab_planes(lat, slabbuf, r * nz, nz);
         SN(sn_set_lattice(slab[r], 0, slabbuf));
-        slab_planes(lat, ghost, r * nz - g, g);
-        SN(sn_set_ghost(slab[r], 0, 0, ghost));
-        slab_planes(lat, ghost, (r + 1) * nz, g);
-        SN(sn_set_ghost(slab[r], 0, 1, ghost));
     }
     for (r = 0; r < ngpus; r++) {
         SN(sn_attach_peer(slab[r], 0, slab[(r + ngpus - 1) % ngpus]));
         SN(sn_attach_peer(slab[r], 1, slab[(r + 1) % ngpus]));
     }
-    free(ghost);
+    for (r = 0; r < ngpus; r++) SN(sn_pull_ghosts(slab[r]));               /* ghost planes, GPU to GPU */
+    SN(sn_kernel_in_use(slab[0], &k));
+    slabs_tiled = (k == SN_KERNEL_TILED);
     fprintf(stderr, "Z-slab decomposition: %d GPUs x %d planes, devices %d..%d\n", ngpus, nz, device, device + ngpus - 1);
 }
 
 static void engine_sweeps(sn_handle *h, long long n)                       /* MC_moves(MCMinorSteps), main.c:222,248 */
 {
-    int r;
+    int r; long long done, chunk;
     if (ngpus == 1) { SN(sn_mc_sweeps(h, n)); return; }
-    for (r = 0; r < ngpus; r++) SN(sn_mc_sweeps(slab[r], n));             /* asynchronous: the slabs run concurrently */
-    analysis_stale = 1;
+    /* The slabs run concurrently and wait for each other on the device.  The tiled kernel is one launch per call.  The
+     * colour passes are ~200 launches per sweep and slab, each colour waiting for the neighbours' previous one: queued a
+     * whole mega-step at a time from this one thread, slab 0's launches would fill the launch queue before slab 1 has
+     * queued anything -- so they go in rounds of one sweep per slab. */
+    chunk = slabs_tiled ? n : 1;
+    for (done = 0; done < n; done += chunk)
+        for (r = 0; r < ngpus; r++) SN(sn_mc_sweeps(slab[r], n - done < chunk ? n - done : chunk));
 }
 
 static void engine_sync(sn_handle *h)
@@ -304,7 +313,7 @@ static void engine_sync(sn_handle *h)
 static void engine_set_efield(sn_handle *h, const float E[3])
 {
     int r;
-    for (r = 0; r < (nT > 1 ? nT : 1); r++) SN(sn_set_efield(h, r, E));
+    for (r = 0; r < (ngpus == 1 ? (nT > 1 ? nT : 1) : 0); r++) SN(sn_set_efield(h, r, E));
     for (r = 0; r < (ngpus > 1 ? ngpus : 0); r++) SN(sn_set_efield(slab[r], 0, E));
 }
 
@@ -324,33 +333,52 @@ static void engine_counters(sn_handle *h, unsigned long long *acc, unsigned long
     for (r = 0; r < ngpus; r++) { SN(sn_get_counters(slab[r], 0, &a, &b, &c)); *acc += a; *rej += b; *vac += c; }
 }
 
-/* bring the full-lattice analysis handle up to date with the slabs (no-op on one GPU) */
-static void engine_gather(sn_handle *h)
+/* the lattice in host order (dumps, checkpoints): one handle, or the slabs' planes put side by side */
+static void engine_get_lattice(sn_handle *h, float *lat)
 {
     int r, x, y; const int nz = Z / ngpus;
-    if (ngpus == 1 || !analysis_stale) return;
+    if (ngpus == 1) { SN(sn_get_lattice(h, cur, lat)); return; }
     for (r = 0; r < ngpus; r++) {
         SN(sn_get_lattice(slab[r], 0, slabbuf));
         for (x = 0; x < X; x++) for (y = 0; y < Y; y++)
-            memcpy(latbuf + site(x, y, r * nz) * 4, slabbuf + ((size_t)x * Y + y) * nz * 4, (size_t)nz * 4 * sizeof(float));
+            memcpy(lat + site(x, y, r * nz) * 4, slabbuf + ((size_t)x * Y + y) * nz * 4, (size_t)nz * 4 * sizeof(float));
     }
-    SN(sn_set_lattice(h, 0, latbuf));
-    analysis_stale = 0;
 }
 
-static void refresh_potential(sn_handle *h) { SN(sn_potential_map(h, cur, Vbuf)); }
+static void slab_map_into(double *dst, int r)                              /* slabV[X][Y][nz] -> dst[X][Y][Z] at z0 = r nz */
+{
+    int x, y; const int nz = Z / ngpus;
+    for (x = 0; x < X; x++) for (y = 0; y < Y; y++)
+        memcpy(dst + site(x, y, r * nz), slabV + ((size_t)x * Y + y) * nz, (size_t)nz * sizeof(double));
+}
+
+static void refresh_potential(sn_handle *h)
+{
+    int r;
+    if (ngpus == 1) { SN(sn_potential_map(h, cur, Vbuf)); return; }
+    for (r = 0; r < ngpus; r++) { SN(sn_potential_map(slab[r], 0, slabV)); slab_map_into(Vbuf, r); }
+}
 
 static void do_rdf(sn_handle *h, const char *fn)
 {
     double fe[SN_RDF_BINS], afe[SN_RDF_BINS]; long long cnt[SN_RDF_BINS];
-    SN(sn_rdf(h, cur, fe, afe, cnt));
+    if (ngpus == 1) SN(sn_rdf(h, cur, fe, afe, cnt));
+    else {
+        double f1[SN_RDF_BINS], a1[SN_RDF_BINS]; long long c1[SN_RDF_BINS]; int r, b;
+        for (b = 0; b < SN_RDF_BINS; b++) { fe[b] = afe[b] = 0.0; cnt[b] = 0; }
+        for (r = 0; r < ngpus; r++) {                                       /* sums and counts add up over the slabs */
+            SN(sn_rdf(slab[r], 0, f1, a1, c1));
+            for (b = 0; b < SN_RDF_BINS; b++) { fe[b] += f1[b]; afe[b] += a1[b]; cnt[b] += c1[b]; }
+        }
+    }
     write_rdf(fn, fe, afe, cnt);
 }
 
 static void write_efield_xyz(sn_handle *h, const char *fn, int cutoff, int half_offset)   /* analysis.c:379-389, 468-479 */
 {
-    FILE *fo; int x, y, z;
-    SN(sn_efield_map(h, cur, cutoff, half_offset, Vbuf));
+    FILE *fo; int x, y, z, r;
+    if (ngpus == 1) SN(sn_efield_map(h, cur, cutoff, half_offset, Vbuf));
+    else for (r = 0; r < ngpus; r++) { SN(sn_efield_map(slab[r], 0, cutoff, half_offset, slabV)); slab_map_into(Vbuf, r); }
     fo = fopen(fn, "w");
     if (!fo) { perror(fn); return; }
     for (x = 0; x < X; x++) for (y = 0; y < Y; y++) for (z = 0; z < Z; z++) fprintf(fo, "%d %d %d %f\n", x, y, z, Vbuf[site(x, y, z)]);
@@ -360,7 +388,12 @@ static void write_efield_xyz(sn_handle *h, const char *fn, int cutoff, int half_
 static void do_recombination(sn_handle *h, FILE *log)                      /* analysis.c:96-228 */
 {
     double r[SN_RECOMB_N];
-    SN(sn_recombination(h, cur, r));
+    if (ngpus == 1) SN(sn_recombination(h, cur, r));
+    else {
+        double parts[16 * SN_RECOMB_PARTIAL_N]; int k;
+        for (k = 0; k < ngpus; k++) SN(sn_recombination_partial(slab[k], 0, parts + k * SN_RECOMB_PARTIAL_N));
+        SN(sn_recombination_finish(ngpus, parts, r));
+    }
     if (log) {
         fprintf(log, "T: %d ZBe: %e ZBh: %e ZFDe: %e ZFDh: %e R_Boltz: %e ", T, r[0], r[1], r[2], r[3], r[4]);
         fprintf(log, "R_FD: %e FD-Total-electron: %e FD-Total-hole: %e\n", r[5], r[6], r[7]);
@@ -389,7 +422,7 @@ static void analysis_initial(sn_handle *h)                                 /* ma
     if (need_v) refresh_potential(h);
     if (CalculatePotential) write_potential_xyz("initial_lattice_potential.xyz", Vbuf);
     if (SavePotentialCube) write_potential_cube("initial_lattice_potential.cube", Vbuf);
-    if (SaveDipolesSVG || SaveDipolesPNG || SaveDipolesXYZ) SN(sn_get_lattice(h, cur, latbuf));
+    if (SaveDipolesSVG || SaveDipolesPNG || SaveDipolesXYZ) engine_get_lattice(h, latbuf);
     if (SaveDipolesSVG) write_lattice_svg("initial-SVG.svg", latbuf);
     if (CalculatePotential) write_potential_png("initial_pot.png", Vbuf);
     if (SaveDipolesXYZ) write_lattice_xyz("initial_dipoles.xyz", latbuf);
@@ -404,7 +437,6 @@ static void analysis_midpoint(sn_handle *h, int MCstep, FILE *log)         /* ma
     char name[160], prefix[100];
     int need_v = CalculatePotential || SavePotentialCube || DisplayDumbTerminal;
     sprintf(prefix, "T_%04d_%d_%03d", T, (int)CageStrain, MCstep);       /* main.c:58 */
-    engine_gather(h);
     if (need_v) refresh_potential(h);
     if (DisplayDumbTerminal) terminal_summary();
     if (CalculateRecombination) do_recombination(h, log);                                   /* main.c:73 */
@@ -419,7 +451,7 @@ static void analysis_midpoint(sn_handle *h, int MCstep, FILE *log)         /* ma
     if (SavePotentialCube) write_potential_cube(name, Vbuf);
     sprintf(name, "%s_potential.png", prefix);
     if (CalculatePotential) write_potential_png(name, Vbuf);
-    if (SaveDipolesPNG || SaveDipolesSVG) SN(sn_get_lattice(h, cur, latbuf));
+    if (SaveDipolesPNG || SaveDipolesSVG) engine_get_lattice(h, latbuf);
     sprintf(name, "%s_MC-PNG.png", prefix);
     if (SaveDipolesPNG) write_lattice_ppm_hsv(name, latbuf);
     sprintf(name, "%s_MC-SVG.svg", prefix);
@@ -442,8 +474,8 @@ static void checkpoint_write(sn_handle *h, unsigned long long seed, int next_meg
     memset(&hd, 0, sizeof hd);
     memcpy(hd.magic, "SNB200C1", 8);
     hd.X = X; hd.Y = Y; hd.Z = Z; hd.T = T; hd.seed = seed; hd.next_megastep = next_megastep;
-    if (ngpus > 1) { analysis_stale = 1; engine_gather(h); SN(sn_get_sweep_count(slab[0], &hd.sweeps)); }   /* gather fills latbuf */
-    else { SN(sn_get_lattice(h, 0, latbuf)); SN(sn_get_sweep_count(h, &hd.sweeps)); }
+    engine_get_lattice(h, latbuf);
+    SN(sn_get_sweep_count(ngpus > 1 ? slab[0] : h, &hd.sweeps));
     engine_counters(h, &hd.accept, &hd.reject, &hd.vacant);
     snprintf(tmp, sizeof tmp, "%s.tmp", checkpoint_path);
     f = fopen(tmp, "wb");
@@ -531,9 +563,10 @@ int main(int argc, char *argv[])
             return 0;
         }
         sprintf(name, "Recombination_T_%04d.log", T);                      /* main.c:165-178 */
-        log = fopen(name, "w");
+        log = fopen(name, restart_path ? "a" : "w");                       /* a resumed run keeps the lines of the mega-steps before the checkpoint */
         fprintf(stderr, "Log file '%s' opened. ", name);
-        if (log) fprintf(log, "# Starrynight - simulation run on time(NULL)= %ld\n# Mersenne Twister Seed: %X\n", (long)time(NULL), SEED);
+        if (log && !restart_path) fprintf(log, "# Starrynight - simulation run on time(NULL)= %ld\n# Mersenne Twister Seed: %X\n", (long)time(NULL), SEED);
+        if (log && restart_path) fprintf(log, "# restarted from '%s' at mega-step %d on time(NULL)= %ld\n", restart_path, ck.next_megastep, (long)time(NULL));
 
         SN(sn_default_params(&p));
         p.X = X; p.Y = Y; p.Z = Z; p.cutoff = DipoleCutOff; p.CageStrain = CageStrain; p.K = K;
@@ -542,11 +575,10 @@ int main(int argc, char *argv[])
         p.ConstrainToX = ConstrainToX; p.DIM = DIM; p.nreplicas = nT; p.seed = SEED; p.device = device; p.kernel = kernel;
         logs[0] = log;
     }
-    if (ngpus > 1) { slabs_create(&p, latbuf); p.kernel = SN_KERNEL_COLOUR; }   /* the full-lattice handle only analyses */
-    SN(sn_create(&p, &h));                                                 /* lattice malloc + gen_neighbour, main.c:155-180 */
-    { int nnb = 0; SN(sn_neighbour_table(h, &nnb, NULL, NULL));
+    if (ngpus > 1) slabs_create(&p, latbuf);                               /* one Z-slab handle per GPU, no full-lattice handle */
+    else { SN(sn_create(&p, &h)); SN(sn_set_lattice(h, 0, latbuf)); }      /* lattice malloc + gen_neighbour, main.c:155-180 */
+    { int nnb = 0; SN(sn_neighbour_table(ngpus > 1 ? slab[0] : h, &nnb, NULL, NULL));
       fprintf(stderr, "\nNeighbour list generated: %d neighbours found with DipoleCutOff=%d.\n", nnb, DipoleCutOff); }
-    SN(sn_set_lattice(h, 0, latbuf));
     for (r = 1; r < nT; r++) {
         /* the other temperatures of the batch: initial state, seed and log of a separate run at Ts[r] (main.c:165-215) */
         const unsigned int SEED = (unsigned int)(0xDEADBEEFu + (unsigned int)Ts[r]);
@@ -562,7 +594,7 @@ int main(int argc, char *argv[])
     }
     if (nT > 1) fprintf(stderr, "Temperature batch: %d replicas, T = %d .. %d\n", nT, Ts[0], Ts[nT - 1]);
     if (restart_path) {
-        SN(sn_set_sweep_count(h, ck.sweeps));
+        if (ngpus == 1) SN(sn_set_sweep_count(h, ck.sweeps));
         SN(sn_set_counters(ngpus > 1 ? slab[0] : h, 0, ck.accept, ck.reject, ck.vacant));
         for (r = 0; r < (ngpus > 1 ? ngpus : 0); r++) SN(sn_set_sweep_count(slab[r], ck.sweeps));
         first_megastep = ck.next_megastep;
@@ -577,11 +609,10 @@ int main(int argc, char *argv[])
     if (restart_path) goto production;
     for (i = 0; i < MCEqmSteps; i++) { fprintf(stderr, ","); engine_sweeps(h, sweeps_per_megastep); }   /* main.c:219-223 */
     engine_sync(h);
-    if (CalculateEfield || CalculatePotential || SaveDipolesSVG) engine_gather(h);
     for (cur = 0; cur < nT; cur++) {                                                        /* untagged files: the last T wins */
         if (CalculateEfield) write_efield_xyz(h, "equilib_lattice_efield.xyz", 4, 0);       /* main.c:225 */
         if (CalculatePotential) { refresh_potential(h); write_potential_png("equilib_pot.png", Vbuf); }
-        if (SaveDipolesSVG) { SN(sn_get_lattice(h, cur, latbuf)); write_lattice_svg("equilib-SVG.svg", latbuf); }
+        if (SaveDipolesSVG) { engine_get_lattice(h, latbuf); write_lattice_svg("equilib-SVG.svg", latbuf); }
     }
     cur = 0;
 
@@ -623,8 +654,8 @@ production:
     }
     fprintf(stderr, " For us, there is only the trying. The rest is not our business. ~T.S.Eliot\n\n");
     for (r = 0; r < nT; r++) if (logs[r]) fclose(logs[r]);
-    SN(sn_destroy(h));
+    if (h) SN(sn_destroy(h));
     for (i = 0; i < (ngpus > 1 ? ngpus : 0); i++) SN(sn_destroy(slab[i]));
-    free(latbuf); free(Vbuf); free(slabbuf);
+    free(latbuf); free(Vbuf); free(slabbuf); free(slabV);
     return 0;
 }

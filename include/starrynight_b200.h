@@ -90,6 +90,9 @@ typedef struct {
 SN_API const char *sn_last_error(void);
 SN_API const char *sn_version(void);
 
+/* CUDA devices this process can use (0 without a GPU; sn_create then fails: there is no CPU path) */
+SN_API int sn_device_count(int *n);
+
 /* fills *p with the reference's defaults (config.c:12-93): 20^3, cutoff 3, ... */
 SN_API int sn_default_params(sn_params *p);
 

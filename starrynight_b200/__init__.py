@@ -26,7 +26,7 @@ SN_KERNEL_AUTO, SN_KERNEL_COLOUR, SN_KERNEL_TILED, SN_KERNEL_TILED_PHASED, SN_KE
 SN_RDF_BINS = 81
 
 EXPORTS = [
-    "sn_last_error", "sn_version", "sn_default_params", "sn_create", "sn_destroy", "sn_neighbour_table",
+    "sn_last_error", "sn_version", "sn_device_count", "sn_default_params", "sn_create", "sn_destroy", "sn_neighbour_table",
     "sn_set_lattice", "sn_get_lattice", "sn_set_lattice_async", "sn_get_lattice_async", "sn_order_after", "sn_pull_ghosts", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_set_replica_cagestrain", "sn_mc_sweeps", "sn_mc_sweep_audit",
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_set_counters",
     "sn_get_sweep_count", "sn_set_sweep_count", "sn_set_replica_seed", "sn_site_energy",
@@ -62,6 +62,7 @@ def load_library() -> C.CDLL:
     lib.sn_last_error.restype = C.c_char_p
     lib.sn_version.restype = C.c_char_p
     H = C.c_void_p
+    lib.sn_device_count.argtypes = [C.POINTER(C.c_int)]
     lib.sn_create.argtypes = [C.POINTER(sn_params), C.POINTER(H)]
     lib.sn_destroy.argtypes = [H]
     lib.sn_neighbour_table.argtypes = [H, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]

@@ -34,6 +34,15 @@ int sn_fail(int code, const char *fmt, ...)
 extern "C" const char *sn_last_error(void) { return sn_err; }
 extern "C" const char *sn_version(void) { return "starrynight_b200 0.1 (sm_100a)"; }
 
+extern "C" int sn_device_count(int *n)
+{
+    if (!n) return sn_fail(SN_ERR_INVALID, "sn_device_count: null");
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+    *n = c;
+    return SN_OK;
+}
+
 extern "C" int sn_default_params(sn_params *p)
 {
     if (!p) return sn_fail(SN_ERR_INVALID, "sn_default_params: null");

@@ -132,17 +132,20 @@ def test_driver_efield_maps_and_recombination_log(built, tmp_path):
 
 
 @pytest.mark.gpu
-def test_driver_two_gpu_slabs_write_identical_files(built, tmp_path):
-    """GPUs = 2 (Z-slabs, boundary pushes over NVLink) must reproduce the single-GPU run file for file:
-    the decomposed chain is bit-identical and the analysis runs on the gathered lattice."""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("kern", ["auto", "colour"])
+def test_driver_two_gpu_slabs_write_identical_files(built, tmp_path, kern):
+    """GPUs = 2 (Z-slabs, boundary pushes over NVLink) must reproduce the single-GPU run file for file: the decomposed
+    chain is bit-identical and the analysis runs on the slabs themselves (no gather).  On a one-GPU box both slabs share
+    the device.  Kernel = "colour" with many sweeps per mega-step is the case where one host thread must not queue a
+    whole mega-step per slab (the launch queue would fill before the second slab has queued anything)."""
     cfg = ref_files()["starrynight.cfg"].decode()
     cfg = cfg.replace("X=20", "X=32").replace("Y=20", "Y=32").replace("Z=28", "Z=64").replace('"antiferro_wall"', '"random"')
-    cfg = cfg.replace("MCMegaSteps: 1", "MCMegaSteps: 2").replace("MCMoves: 2.0", "MCMoves: 3.0")
-    assert "MCMegaSteps: 2" in cfg and "MCMoves: 3.0" in cfg and "Z=64" in cfg
+    moves = "24.0" if kern == "colour" else "3.0"
+    cfg = cfg.replace("MCMegaSteps: 1", "MCMegaSteps: 2").replace("MCMoves: 2.0", f"MCMoves: {moves}")
+    assert "MCMegaSteps: 2" in cfg and f"MCMoves: {moves}" in cfg and "Z=64" in cfg
     cfg += '\nHysteresis : { amplitude = 0.1; steps = 2; cycles = 1; };\n'
+    if kern == "colour":
+        cfg += 'Kernel = "colour";\n'
     outs = []
     for n in (1, 2):
         d = tmp_path / f"gpus{n}"
@@ -176,6 +179,8 @@ def test_driver_checkpoint_restart_continues_the_chain(built, tmp_path, shape):
         d = tmp_path / name
         d.mkdir()
         (d / "starrynight.cfg").write_text(cfg.replace("MCMegaSteps: 1", f"MCMegaSteps: {steps}") + "\n" + extra + "\n")
+        if name == "resumed":                          # the normal use: resume where the first run left its files
+            (d / "Recombination_T_0300.log").write_text((runs["first"][0] / "Recombination_T_0300.log").read_text())
         run = subprocess.run([DRIVER], cwd=d, capture_output=True, text=True)
         assert run.returncode == 0, run.stderr[-2000:]
         runs[name] = (d, [l for l in run.stderr.splitlines() if "ACCEPT:" in l][0])
@@ -186,6 +191,10 @@ def test_driver_checkpoint_restart_continues_the_chain(built, tmp_path, shape):
             assert (runs["full"][0] / fn).read_bytes() == (runs["resumed"][0] / fn).read_bytes(), fn
     assert not (runs["resumed"][0] / "T_0300_1_001_potential.xyz").exists()      # resumed at mega-step 2
     assert runs["full"][1] == runs["resumed"][1]                                   # counters carried over
+    # the resumed run appends to the log of the interrupted one instead of truncating it
+    first_log = (runs["first"][0] / "Recombination_T_0300.log").read_text()
+    resumed_log = (runs["resumed"][0] / "Recombination_T_0300.log").read_text()
+    assert resumed_log.startswith(first_log) and "# restarted from" in resumed_log[len(first_log):]
 
 
 @pytest.mark.gpu

@@ -91,3 +91,76 @@ def test_efield_maps_and_recombination_against_golden(sn, name):
     assert np.allclose(got[:8], ref, rtol=1.5e-6)                            # the log holds 7 digits
     full = oa.Oracle("f64").recombination(p, lat)
     assert np.allclose(got, full, rtol=1e-11)
+
+
+@pytest.fixture(scope="module")
+def devices():
+    import torch
+    n = torch.cuda.device_count()
+    return list(range(min(n, 8))) if n >= 2 else [0]
+
+
+@pytest.mark.parametrize("shape,nslab,kernel", [((64, 32, 64), 2, "tiled"), ((20, 16, 36), 3, "colour"), ((32, 32, 128), 4, "tiled")])
+def test_slab_native_observables_equal_the_whole_lattice(sn, devices, shape, nslab, kernel):
+    """north_star parts (2)+(3): radial_order_parameter (analysis.c:528-598), dipole_potential (:65-94), the E-field maps
+    (:310-465) and the recombination sums (:96-170) evaluated on a Z-slab decomposed lattice -- each slab over its own
+    sites, planes beyond the slab read from the neighbouring slabs' device memory -- against one handle holding the
+    whole lattice, after sweeps (so the slabs' data is what the sweep kernels and their halo pushes left behind)."""
+    X, Y, Z = shape
+    kid = sn.SN_KERNEL_TILED if kernel == "tiled" else sn.SN_KERNEL_COLOUR
+    lat = oa.random_lattice(X, Y, Z, seed=33, lengths=(1.0, 0.5, 0.0), prevalence=(0.7, 0.2, 0.1))
+    with sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.05, 0, 0), seed=9, kernel=kid) as one:
+        one.set_lattice(lat)
+        one.MC_sweeps(2)
+        fe, afe, cnt = one.radial_order_parameter()
+        V = one.dipole_potential()
+        E4 = one.dipole_electricfield(4, False)
+        E2 = one.dipole_electricfield(2, True)
+        rec = one.recombination()
+        P = one.polarisation()
+    nz = Z // nslab
+    sims = [sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.05, 0, 0), seed=9, device=devices[r % len(devices)], z0=r * nz, nz=nz, kernel=kid)
+            for r in range(nslab)]
+    try:
+        for r, s in enumerate(sims):
+            s.set_lattice(lat[:, :, r * nz:(r + 1) * nz])
+        for r, s in enumerate(sims):
+            s.attach_peer(0, sims[(r - 1) % nslab]); s.attach_peer(1, sims[(r + 1) % nslab])
+        for s in sims:
+            s.pull_ghosts()
+        for s in sims:
+            s.MC_sweeps(2)
+        parts = [s.radial_order_parameter() for s in sims]
+        assert np.array_equal(sum(q[2] for q in parts), cnt)
+        assert np.allclose(sum(q[0] for q in parts), fe, rtol=1e-12, atol=1e-9)
+        assert np.allclose(sum(q[1] for q in parts), afe, rtol=1e-12, atol=1e-9)
+        assert np.array_equal(np.concatenate([s.dipole_potential() for s in sims], axis=2), V)      # same terms in the same order
+        assert np.array_equal(np.concatenate([s.dipole_electricfield(4, False) for s in sims], axis=2), E4)
+        assert np.array_equal(np.concatenate([s.dipole_electricfield(2, True) for s in sims], axis=2), E2)
+        got = sn.recombination_finish([s.recombination_partial() for s in sims])
+        assert np.allclose(got, rec, rtol=1e-12)
+        assert np.allclose(sum(np.asarray(s.polarisation()) * s.nsites for s in sims) / (X * Y * Z), P, rtol=1e-12, atol=1e-15)
+        with pytest.raises(sn.SnError, match="sn_recombination_partial"):
+            sims[0].recombination()
+    finally:
+        for s in sims:
+            s.close()
+
+
+def test_observable_kernels_cover_ragged_and_tiny_lattices(sn):
+    """Extents that are not multiples of the 8^3 observable tile, and extents smaller than the stencil radius (images
+    repeat, as the reference's % arithmetic does): against the f64 oracle."""
+    for (X, Y, Z) in [(13, 9, 11), (5, 4, 3), (17, 8, 1)]:
+        p = oa.make_params(X, Y, Z, 3, 1.0, 0.0, (0, 0, 0), 1.0)
+        lat = oa.random_lattice(X, Y, Z, seed=X, lengths=(1.0, 0.5), prevalence=(0.7, 0.3))
+        o = oa.Oracle("f64")
+        with sim_for(sn, p, lat) as sim:
+            V = sim.dipole_potential().ravel()
+            ref = o.potential_map(p, lat)
+            assert np.max(np.abs(V - ref)) < 1e-11 * max(1.0, np.max(np.abs(ref)))
+            fe, afe, cnt = sim.radial_order_parameter()
+            ofe, oafe, ocnt = o.rdf(p, lat)
+            assert np.array_equal(cnt, ocnt.astype(np.int64))
+            assert np.allclose(fe, ofe, rtol=1e-11, atol=1e-9) and np.allclose(afe, oafe, rtol=1e-11, atol=1e-9)
+            E = sim.dipole_electricfield(4, False).ravel()
+            assert np.allclose(E, o.efield_map(p, lat, 4, False).ravel(), rtol=1e-11, atol=1e-12)
