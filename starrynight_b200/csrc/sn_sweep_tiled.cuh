@@ -276,13 +276,24 @@ __global__ void sn_convert_layout_kernel(float4 *__restrict__ lat, float4 *__res
     if (to_tiled) *b = *a; else *a = *b;
 }
 
+// Tile colours along one axis of n tiles: tiles that are active together must not be neighbours, also across the
+// periodic wrap.  Even n: two colours (parity).  Odd n (>= 3): the last tile gets a colour of its own, the others
+// alternate -- 3 colours.  A sweep visits the ncx * ncy * ncz colour combinations ("phases", 8 to 27) in order.
+__host__ __device__ inline int sn_tc_ncol(int n) { return (n & 1) ? 3 : 2; }
+__host__ __device__ inline int sn_tc_count(int n, int c) { return c < 2 ? (n >> 1) : 1; }
+__host__ __device__ inline int sn_tc_tile(int n, int c, int i) { return c < 2 ? 2 * i + c : n - 1; }
+__host__ __device__ inline int sn_tc_colour(int n, int t) { return ((n & 1) && t == n - 1) ? 2 : (t & 1); }
+
 struct SnTileFlow {
-    int hx, hy, hz;                     // active tiles per axis and phase (= tiles / 2)
+    int tnx, tny, tnz;                  // tiles per axis (own tiles: z ghost layers not counted)
+    int ncx, ncy, ncz, np;              // colours per axis, phases per sweep
+    int periodic_z;                     // the handle owns the whole z axis (ghost version layers mirror its own end tiles)
     int nrep;
+    unsigned int pre[28];               // pre[p] = items of the phases before p within one sweep; pre[np] = items per sweep
     unsigned long long base_sweep;      // sweeps completed before item 0 (the version of every tile at that point)
-    unsigned long long n_begin, n_end;  // items of this launch; item n = ((sweep * 8 + phase) * nrep + replica) * hx*hy*hz + tile
+    unsigned long long n_begin, n_end;  // items of this launch; item n = sweep * pre[np] + pre[phase] + replica * tiles(phase) + tile
     unsigned long long *next;           // work counter (device, zero at launch): item = n_begin + atomicAdd(next, 1)
-    unsigned int *ver;                  // [rep][2hx][2hy][2hz + 2] tile versions; z index shifted by one ghost layer
+    unsigned int *ver;                  // [rep][tnx][tny][tnz + 2] tile versions; z index shifted by one ghost layer
     unsigned int *peer_ver_lo, *peer_ver_hi;   // where my bottom / top tile layer is a ghost layer: the slab neighbours' arrays, or `ver` itself
     int sys_scope;                      // ghost versions and planes are written by other GPUs
     float *audit;                       // AUDIT instantiation: one record per attempt (sn_audit_write), else unused
@@ -292,7 +303,7 @@ struct SnTileFlow {
 
 struct __align__(16) SnTileItem {
     int x0, y0, z0, rep;                // tile origin (slab-local z) and replica
-    int tx, ty, tz, p;                  // tile coordinates and phase (px << 2 | py << 1 | pz)
+    int tx, ty, tz, p;                  // tile coordinates and phase ((cx * ncy + cy) * ncz + cz)
     unsigned long long sweep;           // global sweep index = Philox counter word = tile version before the item
     int valid, ready;                   // (scheduler hand-over) item exists; its dependencies were met when polled
 };
@@ -301,26 +312,30 @@ __device__ __forceinline__ SnTileItem sn_tile_item(const SnTileFlow &f, unsigned
 {
     SnTileItem it;
     it.valid = 1; it.ready = 0;
-    const unsigned int P1 = (unsigned int)(f.hx * f.hy * f.hz);
-    const unsigned long long P = (unsigned long long)P1 * f.nrep;
-    const unsigned long long sp = n / P;
-    const unsigned int pos = (unsigned int)(n - sp * P);
-    it.sweep = f.base_sweep + (sp >> 3);
-    it.p = (int)(sp & 7);
+    const unsigned long long S = f.pre[f.np];
+    const unsigned long long sw = n / S;
+    const unsigned int m = (unsigned int)(n - sw * S);
+    int p = 0;
+    while (p + 1 < f.np && m >= f.pre[p + 1]) p++;
+    it.sweep = f.base_sweep + sw;
+    it.p = p;
+    const int cz = p % f.ncz, cy = (p / f.ncz) % f.ncy, cx = p / (f.ncz * f.ncy);
+    const int kx = sn_tc_count(f.tnx, cx), ky = sn_tc_count(f.tny, cy), kz = sn_tc_count(f.tnz, cz);
+    const unsigned int P1 = (unsigned int)(kx * ky * kz), pos = m - f.pre[p];
     it.rep = (int)(pos / P1);
-    const int r = (int)(pos % P1), iz = r % f.hz, iy = (r / f.hz) % f.hy;
+    const int r = (int)(pos % P1), iz = r % kz, iy = (r / kz) % ky;
     // The x order is rotated by one tile plane per sweep: the wrap-around neighbour (ix - 1 of ix = 0) would
     // otherwise be the last plane of the previous sweep, i.e. a barrier per sweep; rotated, every dependency
     // of an item lies at least ~a phase back in the order.
-    const int ix = (r / (f.hz * f.hy) + (int)(it.sweep % (unsigned)f.hx)) % f.hx;
-    it.tx = 2 * ix + ((it.p >> 2) & 1); it.ty = 2 * iy + ((it.p >> 1) & 1); it.tz = 2 * iz + (it.p & 1);
+    const int ix = (r / (kz * ky) + (int)(it.sweep % (unsigned)kx)) % kx;
+    it.tx = sn_tc_tile(f.tnx, cx, ix); it.ty = sn_tc_tile(f.tny, cy, iy); it.tz = sn_tc_tile(f.tnz, cz, iz);
     it.x0 = it.tx * snt::T; it.y0 = it.ty * snt::T; it.z0 = it.tz * snt::T;
     return it;
 }
 
 __device__ __forceinline__ long long sn_ver_index(const SnTileFlow &f, int rep, int tx, int ty, int tzg)
 {
-    return (((long long)rep * (2 * f.hx) + tx) * (2 * f.hy) + ty) * (2 * f.hz + 2) + tzg;
+    return (((long long)rep * f.tnx + tx) * f.tny + ty) * (f.tnz + 2) + tzg;
 }
 
 // Warp-collective: have the 26 neighbouring tiles of `it` reached the version that precedes it?
@@ -330,14 +345,18 @@ __device__ __forceinline__ bool sn_tile_deps_ready(const SnTileFlow &f, const Sn
     if (lane < 27 && lane != 13) {
         const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
         int ntx = it.tx + dx, nty = it.ty + dy;
-        const int ntz = it.tz + dz;                                   // -1 .. 2hz: the ends are ghost layers
-        ntx = ntx < 0 ? ntx + 2 * f.hx : (ntx >= 2 * f.hx ? ntx - 2 * f.hx : ntx);
-        nty = nty < 0 ? nty + 2 * f.hy : (nty >= 2 * f.hy ? nty - 2 * f.hy : nty);
-        const int q = ((ntx & 1) << 2) | ((nty & 1) << 1) | (ntz & 1);
+        const int ntz = it.tz + dz;                                   // -1 .. tnz: the ends are ghost layers
+        ntx = ntx < 0 ? ntx + f.tnx : (ntx >= f.tnx ? ntx - f.tnx : ntx);
+        nty = nty < 0 ? nty + f.tny : (nty >= f.tny ? nty - f.tny : nty);
+        // colour of the z neighbour: a ghost layer stands for the handle's own end tile (periodic) or for the slab
+        // neighbour's boundary layer (slabs have an even number of tile layers, globally and each: parity)
+        const int wz = ntz < 0 ? ntz + f.tnz : (ntz >= f.tnz ? ntz - f.tnz : ntz);
+        const int qz = f.periodic_z ? sn_tc_colour(f.tnz, wz) : (ntz & 1);
+        const int q = (sn_tc_colour(f.tnx, ntx) * f.ncy + sn_tc_colour(f.tny, nty)) * f.ncz + qz;
         const unsigned int need = (unsigned int)it.sweep + (q < it.p ? 1u : 0u);
         const unsigned int *src = f.ver + sn_ver_index(f, it.rep, ntx, nty, ntz + 1);
         unsigned int v;
-        if (f.sys_scope && (ntz < 0 || ntz >= 2 * f.hz)) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        if (f.sys_scope && (ntz < 0 || ntz >= f.tnz)) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
         else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
         ok = (int)(v - need) >= 0;
     }
@@ -349,8 +368,8 @@ __device__ __forceinline__ void sn_tile_publish(const SnTileFlow &f, const SnTil
 {
     const unsigned int v = (unsigned int)it.sweep + 1u;
     unsigned int *own = f.ver + sn_ver_index(f, it.rep, it.tx, it.ty, it.tz + 1);
-    unsigned int *glo = it.tz == 0 ? f.peer_ver_lo + sn_ver_index(f, it.rep, it.tx, it.ty, 2 * f.hz + 1) : nullptr;
-    unsigned int *ghi = it.tz == 2 * f.hz - 1 ? f.peer_ver_hi + sn_ver_index(f, it.rep, it.tx, it.ty, 0) : nullptr;
+    unsigned int *glo = it.tz == 0 ? f.peer_ver_lo + sn_ver_index(f, it.rep, it.tx, it.ty, f.tnz + 1) : nullptr;
+    unsigned int *ghi = it.tz == f.tnz - 1 ? f.peer_ver_hi + sn_ver_index(f, it.rep, it.tx, it.ty, 0) : nullptr;
     if (f.sys_scope && (glo || ghi)) {
         // a boundary tile: its pushes into the neighbour GPU's ghost planes (fenced at GPU scope by the
         // threads that made them, observed here through the arrival counter) become visible system-wide
@@ -735,7 +754,8 @@ bool sn_tiled_supported(const sn_handle *h, std::string *why)
     const char *msg = nullptr;
     if (h->p.cutoff != 3) msg = "DipoleCutOff must be 3";
     else if (G.Z == 1) msg = "lattice is flat (Z == 1)";
-    else if (G.X % 32 || G.Y % 32 || G.nz % 32 || G.z0 % 32) msg = "X, Y, slab height and slab origin must be multiples of 32";
+    else if (G.X % 16 || G.Y % 16 || G.nz % 16 || G.X < 32 || G.Y < 32 || G.nz < 32) msg = "X, Y and Z must be multiples of 16, at least 32";
+    else if (!G.periodic_z && (G.nz % 32 || G.z0 % 32 || G.Z % 32)) msg = "Z-slabs: Z, slab height and slab origin must be multiples of 32";
     if (msg) { if (why) *why = msg; return false; }
     return true;
 }
@@ -816,7 +836,15 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
     SnSweepArgs a = sn_sweep_args(h);
     a.lat = h->lat2;                                  // the kernel works on the de-interleaved copies (own and neighbours')
     SnTileFlow f;
-    f.hx = G.X / 32; f.hy = G.Y / 32; f.hz = G.nz / 32; f.nrep = h->p.nreplicas;
+    f.tnx = G.X / snt::T; f.tny = G.Y / snt::T; f.tnz = G.nz / snt::T; f.nrep = h->p.nreplicas;
+    f.ncx = sn_tc_ncol(f.tnx); f.ncy = sn_tc_ncol(f.tny); f.ncz = sn_tc_ncol(f.tnz); f.np = f.ncx * f.ncy * f.ncz;
+    f.periodic_z = G.periodic_z;
+    f.pre[0] = 0;
+    for (int p = 0; p < f.np; p++) {
+        const int cz = p % f.ncz, cy = (p / f.ncz) % f.ncy, cx = p / (f.ncz * f.ncy);
+        f.pre[p + 1] = f.pre[p] + (unsigned int)(sn_tc_count(f.tnx, cx) * sn_tc_count(f.tny, cy) * sn_tc_count(f.tnz, cz) * f.nrep);
+    }
+    for (int p = f.np + 1; p < 28; p++) f.pre[p] = f.pre[f.np];
     f.base_sweep = h->sweep;
     f.next = reinterpret_cast<unsigned long long *>(h->flags + SN_FLAGS_NEXT);
     f.ver = h->flags + SN_FLAGS_VER;
@@ -826,7 +854,7 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
     f.audit = h->audit_dev;
     f.err = h->flags + SN_FLAGS_ERR;
     f.timeout_ns = h->spin_timeout_ns;
-    const unsigned long long P = (unsigned long long)f.hx * f.hy * f.hz * f.nrep;      // items per phase
+    const unsigned long long S = f.pre[f.np];                                         // items per sweep
     auto launch = [&](unsigned long long n0, unsigned long long n1) -> int {
         f.n_begin = n0; f.n_end = n1;
         SN_CUDA_CHECK(cudaMemsetAsync(f.next, 0, sizeof(unsigned long long), h->stream));
@@ -841,10 +869,11 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
         return SN_OK;
     };
     if (h->p.kernel == SN_KERNEL_TILED_PHASED) {
-        // validation mode: one launch per tile-parity phase (stream order = barrier between phases)
-        for (unsigned long long sp = 0; sp < 8ULL * (unsigned long long)nsweeps; sp++) { int rc = launch(sp * P, (sp + 1) * P); if (rc) return rc; }
+        // validation mode: one launch per tile-colour phase (stream order = barrier between phases)
+        for (unsigned long long sw = 0; sw < (unsigned long long)nsweeps; sw++)
+            for (int p = 0; p < f.np; p++) { int rc = launch(sw * S + f.pre[p], sw * S + f.pre[p + 1]); if (rc) return rc; }
     } else {
-        int rc = launch(0, 8ULL * (unsigned long long)nsweeps * P);
+        int rc = launch(0, (unsigned long long)nsweeps * S);
         if (rc) return rc;
     }
     h->sweep += (unsigned long long)nsweeps;

@@ -189,7 +189,8 @@ def test_equilibrium_observables_match_reference_chain(sn, T, Ex):
 
 
 @pytest.mark.parametrize("shape,reps,calls", [((32, 32, 32), 1, (3,)), ((64, 64, 64), 1, (2, 3)), ((96, 64, 32), 2, (4,)),
-                                              ((160, 96, 64), 1, (3, 1)), ((256, 256, 64), 1, (2,))])
+                                              ((160, 96, 64), 1, (3, 1)), ((256, 256, 64), 1, (2,)),
+                                              ((48, 48, 48), 2, (2, 1)), ((80, 48, 32), 1, (3,)), ((112, 32, 144), 1, (2,))])
 def test_dataflow_launch_equals_barrier_separated_phases(sn, shape, reps, calls):
     """The tiled kernel runs whole sweeps in one launch, ordering adjacent tiles through per-tile version
     counters instead of a barrier per tile-parity phase.  The chain must be bit-identical to the same
@@ -271,6 +272,41 @@ def test_resident_kernel_equals_colour_passes_bit_for_bit(sn, case):
         assert res[0][1][r] == res[1][1][r]
     assert np.array_equal(res[0][2], res[1][2])
     assert not np.array_equal(res[0][0][0][..., :3], lats[0][..., :3])
+
+
+@pytest.mark.parametrize("shape,want", [((48, 48, 48), "tiled"), ((80, 96, 112), "tiled"), ((100, 100, 100), "colour"), ((32, 32, 16), "colour"),
+                                        ((64, 64, 64), "tiled"), ((20, 20, 28), "resident"), ((100, 100, 1), "resident")])
+def test_kernel_selection(sn, shape, want):
+    """SN_KERNEL_AUTO: the tiled kernel takes every cut-off-3 lattice whose extents are multiples of 16 (>= 32) -- an odd
+    number of tiles along an axis gets a third tile colour -- small lattices live in shared memory, the rest runs colour passes."""
+    ids = {"tiled": sn.SN_KERNEL_TILED, "colour": sn.SN_KERNEL_COLOUR, "resident": sn.SN_KERNEL_RESIDENT}
+    with sn.Simulation(*shape) as sim:
+        assert sim.kernel_in_use() == ids[want]
+
+
+def test_odd_tile_counts_match_the_colour_kernel_statistics(sn):
+    """48^3 (3 tiles per axis, 27 tile phases) on the tiled kernel against colour passes: equilibrium energy and
+    acceptance agree within error bars (independent seeds)."""
+    X, R = 48, 6
+    lat0 = oa.random_lattice(X, X, X, seed=72)
+    stats = {}
+    for name, kern in (("tiled", sn.SN_KERNEL_TILED), ("colour", sn.SN_KERNEL_COLOUR)):
+        with sn.Simulation(X, X, X, CageStrain=1.0, Efield=(0.3, 0, 0), beta=1.0, nreplicas=R, seed=950 + len(name), kernel=kern) as sim:
+            for r in range(R):
+                sim.set_lattice(lat0, r)
+            sim.MC_sweeps(60)
+            sim.reset_counters()
+            es = np.zeros((R, 10))
+            for k in range(10):
+                sim.MC_sweeps(4)
+                for r in range(R):
+                    es[r, k] = sim.total_energy(sn.SN_PREC_F32, r).sum() / X ** 3
+            acc = np.array([sim.counters(r)[0] / sum(sim.counters(r)[:2]) for r in range(R)])
+        stats[name] = np.stack([es.mean(1), acc], 1)
+    for col, what in enumerate(("energy per site", "acceptance ratio")):
+        a, b = stats["tiled"][:, col], stats["colour"][:, col]
+        se = np.sqrt(a.var(ddof=1) / R + b.var(ddof=1) / R)
+        assert abs(a.mean() - b.mean()) < 4.5 * se + 1e-4, f"{what}: tiled {a.mean():.5f} vs colour {b.mean():.5f} (se {se:.5f})"
 
 
 def test_resident_kernel_refuses_what_it_cannot_hold(sn):
