@@ -190,17 +190,21 @@ __host__ __device__ inline int tiles(int n) { return (n + T - 1) / T; }
 __device__ __forceinline__ int wrap(int v, int n) { v %= n; return v < 0 ? v + n : v; }
 }
 
-// box cell i -> lattice site; calls put(i, float4)
+// Stage the box [bx0, bx0+nx) x [by0, by0+ny) x [bz0, bz0+nzb) (lattice coordinates before wrapping) through
+// put(cell, float4), cell = (lx * ny + ly) * nzb + lz.  One (x, y) row per warp at a time, the lanes along z (the
+// contiguous direction of the lattice): two integer divisions per row instead of per cell.
 template <class Put>
 __device__ __forceinline__ void sn_load_box(const SnLatView &view, const SnGeom &G, int bx0, int by0, int bz0, int nx, int ny, int nzb, Put &&put)
 {
-    const int cells = nx * ny * nzb;
-    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-        const int lz = i % nzb, ly = (i / nzb) % ny, lx = i / (nzb * ny);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int row = warp; row < nx * ny; row += nwarps) {
+        const int lx = row / ny, ly = row - lx * ny;
         const int x = sno::wrap(bx0 + lx, G.X), y = sno::wrap(by0 + ly, G.Y);
-        int z = bz0 + lz;
-        if (G.periodic_z) z = sno::wrap(z, G.nz);
-        put(i, sn_view_site(view, G, x, y, z));
+        for (int lz = lane; lz < nzb; lz += 32) {
+            int z = bz0 + lz;
+            if (G.periodic_z) z = sno::wrap(z, G.nz);
+            put(row * nzb + lz, sn_view_site(view, G, x, y, z));
+        }
     }
 }
 
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(sno::THREADS, 1) sn_rdf_tiled_kernel(const SnL
     for (int b = 0; b < nbins; b++) {
         const int o0 = first[b], o1 = first[b + 1];
         double v[2] = {0.0, 0.0};
+#pragma unroll 2
         for (int o = o0; o < o1; o++) {
             const SnRdfOffset f = off[o];
 #pragma unroll
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(sno::THREADS, 1) sn_potential_tiled_kernel(con
         const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
         base[s] = ((lx + sno::POT_R) * sno::POT_N + ly + sno::POT_R) * sno::POT_N + lz + sno::POT_R;
     }
+#pragma unroll 4
     for (int o = 0; o < noff; o++) {
         const SnPotOffset f = off[o];
 #pragma unroll
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(sno::THREADS, 1) sn_efield_tiled_kernel(const 
         const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
         base[s] = ((lx + reach) * N + ly + reach) * N + lz + reach;
     }
+#pragma unroll 2
     for (int o = 0; o < noff; o++) {
         const SnEfOffset2 f = off[o];
 #pragma unroll
