@@ -52,15 +52,36 @@ __host__ __device__ inline long long sn_pidx(const SnGeom &G, int x, int y, int 
     return ((long long)(x + G.g) * G.PY + (y + G.g)) * G.PZ + (z + G.gz);
 }
 
-// Layout of the tiled kernel's copy: the same padded (x, y) grid, but each z row is stored as 4
-// residue runs: plane z lives at run (z+4)&3, position (z+4)>>2.  A tile's 28-plane window then
-// starts at an aligned position in every run and a TMA row is 7 consecutive float4 (112 B).
-__host__ __device__ inline int sn_q2(const SnGeom &G) { return (G.nz + 8) / 4; }                  // positions per run
-__host__ __device__ inline long long sn_rep_stride2(const SnGeom &G) { return (long long)(G.X + 2 * G.g) * G.PY * 4 * sn_q2(G); }
+// Layout of the tiled kernel's copy ("split layout"): the same padded (x, y) grid, z padded to PZ2 = nz + 8 planes
+// (plane z lives at row position z + 4: a tile's 28-plane window z0-4 .. z0+23 starts at an even, 16-byte aligned
+// position), and the four floats of a site split over three arrays per replica:
+//     xy  float2[N2]   at float offset 0          (x, y)
+//     z   float [N2]   at float offset 2 N2
+//     len float [N2]   at float offset 3 N2       (never written by a sweep)
+// N2 = PX * PY * PZ2 cells, i.e. 16 N2 bytes per replica -- the size of the float4 array it replaces, so the buffer
+// stays a float4 * whose replica stride is N2.  The tiled kernel loads two consecutive planes of a column with one
+// LDS.128 (xy) + one LDS.64 (z): 12 bytes per site through the shared-memory pipe instead of 16, and nothing at
+// all for the lengths when every site has length 1.  One TMA row is 28 planes = 224 B (xy) / 112 B (z, len).
+__host__ __device__ inline int sn_pz2(const SnGeom &G) { return G.nz + 8; }
+__host__ __device__ inline long long sn_rep_stride2(const SnGeom &G) { return (long long)(G.X + 2 * G.g) * G.PY * sn_pz2(G); }   // cells = float4 units
 __host__ __device__ inline long long sn_pidx2(const SnGeom &G, int x, int y, int z)
 {
-    const int Q = sn_q2(G), zw = z + 4;
-    return (((long long)(x + G.g) * G.PY + (y + G.g)) * 4 + (zw & 3)) * Q + (zw >> 2);
+    return ((long long)(x + G.g) * G.PY + (y + G.g)) * sn_pz2(G) + (z + 4);
+}
+__host__ __device__ inline float4 sn_ld2(const float4 *rep_base, const SnGeom &G, long long cell)
+{
+    const long long n2 = sn_rep_stride2(G);
+    const float *f = reinterpret_cast<const float *>(rep_base);
+    const float2 xy = reinterpret_cast<const float2 *>(f)[cell];
+    return make_float4(xy.x, xy.y, f[2 * n2 + cell], f[3 * n2 + cell]);
+}
+__host__ __device__ inline void sn_st2(float4 *rep_base, const SnGeom &G, long long cell, const float4 v)
+{
+    const long long n2 = sn_rep_stride2(G);
+    float *f = reinterpret_cast<float *>(rep_base);
+    reinterpret_cast<float2 *>(f)[cell] = make_float2(v.x, v.y);
+    f[2 * n2 + cell] = v.z;
+    f[3 * n2 + cell] = v.w;
 }
 
 // One colour sublattice per axis.  Period P = cutoff+1; if the extent is not a
@@ -162,9 +183,9 @@ struct sn_handle {
     bool species_dirty = false;
     bool use_tiled = false;
     bool use_resident = false;          // lattice small enough to live in one CTA's shared memory (sn_sweep_resident.cuh)
-    // The tiled kernel works on a second copy of the lattice whose z axis is de-interleaved by 4
-    // (layout SnGeom2), so that one TMA row is 7 consecutive float4.  `lat` (canonical) and `lat2` are
-    // synchronised lazily: whoever needs one of them converts from the other if it is stale.
+    // The tiled kernel works on a second copy of the lattice in the split layout (sn_pidx2 / sn_ld2 / sn_st2).
+    // `lat` (canonical) and `lat2` are synchronised lazily: whoever needs one of them converts from the other
+    // if it is stale.
     float4 *lat2 = nullptr;
     bool lat_valid = true, lat2_valid = false;
     // slab wiring

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) sn_scatter_kernel(const float4 *__restric
             zs = zp % G.nz; zs += zs < 0 ? G.nz : 0;
         }
         const float4 v = staging[((long long)xs * G.Y + ys) * G.nz + zs];
-        if (TILED) dst[sn_pidx2(G, xp, yp, zp)] = v; else dst[sn_pidx(G, xp, yp, zp)] = v;
+        if (TILED) sn_st2(dst, G, sn_pidx2(G, xp, yp, zp), v); else dst[sn_pidx(G, xp, yp, zp)] = v;
         nonunit |= (xs == xp && ys == yp && zs == zp && v.w != 1.0f);
     }
     if (__any_sync(0xffffffffu, nonunit) && (threadIdx.x & 31) == 0) *species_flag = 1u;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) sn_gather_kernel(const float4 *__restrict
     const long long n = (long long)G.X * G.Y * G.nz;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int z = (int)(i % G.nz), y = (int)((i / G.nz) % G.Y), x = (int)(i / ((long long)G.nz * G.Y));
-        staging[i] = TILED ? src[sn_pidx2(G, x, y, z)] : src[sn_pidx(G, x, y, z)];
+        staging[i] = TILED ? sn_ld2(src, G, sn_pidx2(G, x, y, z)) : src[sn_pidx(G, x, y, z)];
     }
 }
 

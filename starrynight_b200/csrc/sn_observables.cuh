@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) sn_site_energy_f32_kernel(const float4 *_
 // GPUs' lattices over NVLink -- the observables of a decomposed lattice need no gather.
 
 // Where a replica's sites live: the handle's own array, the slab neighbours' (same geometry), in the canonical
-// padded layout or the tiled kernel's de-interleaved one.
+// padded layout or the tiled kernel's split one.
 struct SnLatView {
     const float4 *own, *lo, *hi;        // replica bases; lo / hi = own for a handle that owns the whole Z axis
     int tiled;
@@ -180,7 +180,7 @@ __device__ __forceinline__ float4 sn_view_site(const SnLatView &v, const SnGeom 
 {
     const float4 *b = v.own;            // x, y already wrapped into the lattice; z in [-nz, 2 nz)
     if (z < 0) { b = v.lo; z += G.nz; } else if (z >= G.nz) { b = v.hi; z -= G.nz; }
-    return v.tiled ? b[sn_pidx2(G, x, y, z)] : b[sn_pidx(G, x, y, z)];
+    return v.tiled ? sn_ld2(b, G, sn_pidx2(G, x, y, z)) : b[sn_pidx(G, x, y, z)];
 }
 
 namespace sno {

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) sn_pull_ghosts_kernel(float4 *__restrict_
         const int zsrc = side == 0 ? G.nz - G.gz + dz : dz;              // the same plane among the neighbour's own
         const float4 *src = (side == 0 ? lo : hi) + (long long)rep * rep_stride;
         float4 *dst = mine + (long long)rep * rep_stride;
-        if (TILED) dst[sn_pidx2(G, xp, yp, zdst)] = src[sn_pidx2(G, xp, yp, zsrc)];
+        if (TILED) sn_st2(dst, G, sn_pidx2(G, xp, yp, zdst), sn_ld2(src, G, sn_pidx2(G, xp, yp, zsrc)));
         else dst[sn_pidx(G, xp, yp, zdst)] = src[sn_pidx(G, xp, yp, zsrc)];
     }
 }

@@ -18,14 +18,14 @@
 //     phases overlap at their tails.  Z-slab handles see the neighbouring GPUs'
 //     boundary tile layers as ghost entries of the version array, written by the
 //     peers over NVLink, so there is no cross-GPU barrier either.
-//   * One persistent CTA per SM.  Per tile, one thread
-//     issues four cp.async.bulk.tensor (TMA) loads from the padded float4 lattice:
-//     box 22 x 22 x 28(z) with elementStrides = 4 along z, start shifted by the
-//     residue r = 0..3.  Shared memory therefore holds the tile + halo
-//     de-interleaved in z: box r keeps planes z0-4+r, z0+r, ..., 7 per (x,y).  Lanes
-//     that own sites 4 apart in z (same colour) then read consecutive float4 --
-//     LDS.128 without bank conflicts -- and every neighbour address is
-//     base + compile-time immediate.
+//   * One persistent CTA per SM.  Per tile, one thread issues cp.async.bulk.tensor (TMA) loads of the
+//     22 x 22 x 28(z) halo box from the split copy of the lattice (sn_common.cuh: xy as float2, z and the
+//     lengths as float arrays, natural z order): one box per array, TMA rows of 224 / 112 B.  The lengths are
+//     loaded only when some site has a length != 1.  A thread owns two consecutive z sites that start at an
+//     even plane, so it reads two planes of a neighbour column at a time: one LDS.128 (x,y of both planes) and
+//     one LDS.64 (both z) -- 12 bytes per site through the shared-memory pipe, no bank conflicts (the 8 lanes
+//     of a quarter-warp read 8 consecutive 16-byte pairs, the 16 lanes of a half-warp 16 distinct 8-byte
+//     pairs), and every neighbour address is base + compile-time immediate.
 //   * Inside a tile the 64 site colours are visited as 16 super-passes (cx,cy).
 //     Two lanes own a segment of 4 consecutive z sites of one (x,y) column, i.e.
 //     the four colours (cx,cy,0..3), 2 sites each.  None of the 28 neighbour
@@ -64,13 +64,15 @@ namespace snt {
 constexpr int T = 16;                    // tile edge
 constexpr int H = 3;                     // halo = cut-off
 constexpr int BX = T + 2 * H;            // 22 columns per axis in the box
-constexpr int NQ = 7;                    // z samples per residue box (window of 28 planes)
-constexpr int BOX_F4 = BX * BX * NQ;     // float4 per residue box
-constexpr int BOX_BYTES = BOX_F4 * 16;   // 54208 bytes moved by each TMA
-constexpr int BOX_STRIDE_F4 = 3392;      // 54272 B: box pitch rounded up to 128 B (TMA destination alignment)
+constexpr int NP = 14;                   // plane pairs per column of the box (28 planes: z0-4 .. z0+23)
+constexpr int XY_BYTES = BX * BX * NP * 16;   // 108416: (x,y) of the box, float4 = two planes
+constexpr int Z_BYTES = BX * BX * NP * 8;     // 54208: z (and, in its own box, the lengths), float2 = two planes
+constexpr int OFF_Z = XY_BYTES;               // 847 * 128 (TMA destinations are 128-byte aligned)
+constexpr int OFF_L = OFF_Z + 54272;          // Z_BYTES rounded up to 128
+constexpr int OFF_END = OFF_L + 54272;
 constexpr int NCOL = 14;                  // neighbour column pairs {(dx,dy), (-dx,-dy)} inside the cut-off disc
 constexpr int SITE_THREADS = 128;        // threads of one role; each owns 2 sites per super-pass
-constexpr int OFF_XF = 4 * BOX_STRIDE_F4 * 16;                 // partial fields handed from role B to role A: float2[2 buffers][3][128]
+constexpr int OFF_XF = OFF_END;                 // partial fields handed from role B to role A: float2[2 buffers][3][128]
 constexpr int OFF_XP = OFF_XF + 2 * 3 * SITE_THREADS * 8;      // proposals drawn by role B: float4[2 buffers][2 sites][128]
 constexpr int OFF_BAR = OFF_XP + 2 * 2 * SITE_THREADS * 16;    // mbarrier
 constexpr int OFF_CTL = OFF_BAR + 16;                          // control warp hand-over: SnTileItem (48 B) + two arrival counters
@@ -145,22 +147,43 @@ __host__ __device__ constexpr Col col(int idx)
 }
 }  // namespace snt
 
-template <int IDX>
-__device__ __forceinline__ void sn_tile_load_pair(const float4 *const (&pe)[8], float4 (&wp)[6], float4 (&wm)[6])
+// The thread's view of the shared tile: pointers to the plane pair that holds its own two sites, in the (x,y)
+// box (float4 = x,y of two planes), the z box and the length box (float2 = two planes).
+struct SnTileCol {
+    const float4 *xy;
+    const float2 *z, *l;
+};
+
+// Planes e = -M .. M+1 (relative to the thread's first site) of the column C cells away, as (x, y, z, length):
+// they lie in the plane pairs t = -(M+1)/2 .. (M+1)/2 -- one LDS.128 + one LDS.64 (+ one for the lengths) each.
+template <int C, int M, bool SPECIES, int N>
+__device__ __forceinline__ void sn_tile_load_col(const SnTileCol &tc, float4 (&w)[N])
+{
+    constexpr int LO = (M + 1) / 2;
+    sn_static_for<-LO, LO + 1>([&](auto tcn) {
+        constexpr int t = decltype(tcn)::value;
+#ifdef SN_EXP_NOLOAD      // experiment: no shared-memory traffic, arithmetic only
+        const float4 q = make_float4(C * 0.001f, t * 0.01f, 0.5f, 0.25f);
+        const float2 zz = make_float2(C * 0.002f, t * 0.02f), ll = make_float2(1.0f, 1.0f);
+#else
+        const float4 q = tc.xy[C + t];
+        const float2 zz = tc.z[C + t];
+        float2 ll = make_float2(1.0f, 1.0f);
+        if constexpr (SPECIES) ll = tc.l[C + t];
+#endif
+        if constexpr (2 * t >= -M && 2 * t <= M + 1) w[2 * t + M] = make_float4(q.x, q.y, zz.x, ll.x);
+        if constexpr (2 * t + 1 >= -M && 2 * t + 1 <= M + 1) w[2 * t + 1 + M] = make_float4(q.z, q.w, zz.y, ll.y);
+    });
+}
+
+template <int IDX, bool SPECIES>
+__device__ __forceinline__ void sn_tile_load_pair(const SnTileCol &tc, float4 (&wp)[6], float4 (&wm)[6])
 {
     constexpr snt::Col c = snt::col(IDX);
     constexpr int M = snt::half_height(c.dx * c.dx + c.dy * c.dy);
-    constexpr int C = (c.dx * snt::BX + c.dy) * snt::NQ;
-    sn_static_for<-M, 2 + M>([&](auto ec) {
-        constexpr int E = decltype(ec)::value;
-#ifdef SN_EXP_NOLOAD      // experiment: no shared-memory traffic, arithmetic only
-        wp[E + M] = make_float4(C * 0.001f, E * 0.01f, 0.5f, 1.0f);
-        wm[E + M] = make_float4(C * 0.002f, E * 0.02f, 0.25f, 1.0f);
-#else
-        wp[E + M] = pe[E + 3][C];
-        wm[E + M] = pe[E + 3][-C];
-#endif
-    });
+    constexpr int C = (c.dx * snt::BX + c.dy) * snt::NP;
+    sn_tile_load_col<C, M, SPECIES>(tc, wp);
+    sn_tile_load_col<-C, M, SPECIES>(tc, wm);
 }
 
 template <int IDX, bool SPECIES>
@@ -190,25 +213,25 @@ __host__ __device__ constexpr int next_in(unsigned mask, int idx)
 }  // namespace snt
 
 template <unsigned MASK, int IDX, bool SPECIES>
-__device__ __forceinline__ void sn_tile_gather_chain(const float4 *const (&pe)[8], SnAcc (&A)[2], float4 (&c0)[6], float4 (&c1)[6])
+__device__ __forceinline__ void sn_tile_gather_chain(const SnTileCol &tc, SnAcc (&A)[2], float4 (&c0)[6], float4 (&c1)[6])
 {
     // c0/c1 hold pair IDX (already loaded); load the next pair of the mask, then do the arithmetic of this one
     if constexpr (IDX < snt::NCOL) {
         constexpr int NEXT = snt::next_in(MASK, IDX + 1);
         float4 n0[6], n1[6];
-        if constexpr (NEXT < snt::NCOL) sn_tile_load_pair<NEXT>(pe, n0, n1);
+        if constexpr (NEXT < snt::NCOL) sn_tile_load_pair<NEXT, SPECIES>(tc, n0, n1);
         sn_tile_compute_pair<IDX, SPECIES>(c0, c1, A);
-        if constexpr (NEXT < snt::NCOL) sn_tile_gather_chain<MASK, NEXT, SPECIES>(pe, A, n0, n1);
+        if constexpr (NEXT < snt::NCOL) sn_tile_gather_chain<MASK, NEXT, SPECIES>(tc, A, n0, n1);
     }
 }
 
 // Contribution of the column pairs in MASK -- and of the thread's own column when CENTRE -- to
-// the local fields of the thread's 2 consecutive z sites.  pe[e+3] points at the thread's own
-// column, plane (first site + e); a neighbour column is a compile-time immediate away.  Each
+// the local fields of the thread's 2 consecutive z sites.  tc points at the plane pair of the thread's
+// own two sites; a neighbour column is a compile-time immediate away.  Each
 // column pair (+c, -c) is loaded once for both sites (sliding z window) and combined with the
 // pair symmetry.  The loads of the next pair are issued before the arithmetic of the current one.
 template <unsigned MASK, bool CENTRE, bool SPECIES>
-__device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], float3 (&F)[2], float3 (&G)[2], float4 (&old)[2])
+__device__ __forceinline__ void sn_tile_gather2(const SnTileCol &tc, float3 (&F)[2], float3 (&G)[2], float4 (&old)[2])
 {
     SnAcc A[2];
 #pragma unroll
@@ -216,12 +239,14 @@ __device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], fl
     constexpr int FIRST = snt::next_in(MASK, 0);
     if constexpr (FIRST < snt::NCOL) {
         float4 c0[6], c1[6];
-        sn_tile_load_pair<FIRST>(pe, c0, c1);
-        sn_tile_gather_chain<MASK, FIRST, SPECIES>(pe, A, c0, c1);
+        sn_tile_load_pair<FIRST, SPECIES>(tc, c0, c1);
+        sn_tile_gather_chain<MASK, FIRST, SPECIES>(tc, A, c0, c1);
     }
     if constexpr (CENTRE) {
         // own column: pairs (0,0,+-dz); also yields the current values of the 2 sites
-        const float4 w0 = pe[0][0], w1 = pe[1][0], w2 = pe[2][0], w3 = pe[3][0], w4 = pe[4][0], w5 = pe[5][0], w6 = pe[6][0], w7 = pe[7][0];
+        float4 w[8];
+        sn_tile_load_col<0, 3, SPECIES>(tc, w);
+        const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], w6 = w[6], w7 = w[7];
         old[0] = w3; old[1] = w4;
         sn_accumulate_pair<0, 0, 1, SPECIES>(A[0], w4, w2);
         sn_accumulate_pair<0, 0, 2, SPECIES>(A[0], w5, w1);
@@ -237,43 +262,51 @@ __device__ __forceinline__ void sn_tile_gather2(const float4 *const (&pe)[8], fl
     }
 }
 
-// Store a site of the de-interleaved copy (layout sn_pidx2) and, if it lies within the ghost width of a
-// face, its images: the periodic copies in x / y (/ z when the handle owns the whole axis) and the
-// neighbouring GPUs' ghost planes over NVLink.  Extents are >= 32 here, so a site has at most one
-// image shift per axis: at most 7 images, written with a handful of predicated stores.
-__device__ __forceinline__ void sn_store_site2(float4 *__restrict__ lat2, float4 *__restrict__ peer_lo, float4 *__restrict__ peer_hi,
-                                               const SnGeom &G, int x, int y, int z, const float4 v)
+// Store two consecutive planes (z even, z + 1) of one column of the split copy (layout sn_pidx2: xy and z arrays;
+// the lengths never change) and, if they lie within the ghost width of a face, their images: the periodic copies
+// in x / y (/ z when the handle owns the whole axis) and the neighbouring GPUs' ghost planes over NVLink.  Extents
+// are >= 32 here, so a site has at most one image shift per axis: at most 7 images, written with a handful of
+// predicated stores.  The pair granularity also touches the planes 3 and nz - 4, whose "images" land in the
+// padding planes nz + 3 and -4 that nobody reads.
+__device__ __forceinline__ void sn_store_pair2(float4 *__restrict__ lat2, float4 *__restrict__ peer_lo, float4 *__restrict__ peer_hi,
+                                               const SnGeom &G, const long long n2, int x, int y, int z, const float4 xy, const float2 zz)
 {
-    lat2[sn_pidx2(G, x, y, z)] = v;
+    auto put = [&](float4 *__restrict__ base, int xx, int yy, int zc) {
+        const long long c = sn_pidx2(G, xx, yy, zc) >> 1;
+        base[c] = xy;
+        reinterpret_cast<float2 *>(reinterpret_cast<float *>(base) + 2 * n2)[c] = zz;
+    };
+    put(lat2, x, y, z);
     const int g = G.g, gz = G.gz;
     const int ix = x < g ? G.X : (x >= G.X - g ? -G.X : 0);
     const int iy = y < g ? G.Y : (y >= G.Y - g ? -G.Y : 0);
-    const int iz = z < gz ? G.nz : (z >= G.nz - gz ? -G.nz : 0);
+    const int iz = z < gz ? G.nz : (z + 1 >= G.nz - gz ? -G.nz : 0);
     if ((ix | iy | iz) == 0) return;
-    if (ix) lat2[sn_pidx2(G, x + ix, y, z)] = v;
-    if (iy) lat2[sn_pidx2(G, x, y + iy, z)] = v;
-    if (ix && iy) lat2[sn_pidx2(G, x + ix, y + iy, z)] = v;
+    if (ix) put(lat2, x + ix, y, z);
+    if (iy) put(lat2, x, y + iy, z);
+    if (ix && iy) put(lat2, x + ix, y + iy, z);
     if (iz) {
         // periodic z: images in this array; Z-slab: the same planes live in the neighbour's ghost shell
         float4 *__restrict__ dst = G.periodic_z ? lat2 : (iz > 0 ? peer_lo : peer_hi);
         if (dst) {
-            dst[sn_pidx2(G, x, y, z + iz)] = v;
-            if (ix) dst[sn_pidx2(G, x + ix, y, z + iz)] = v;
-            if (iy) dst[sn_pidx2(G, x, y + iy, z + iz)] = v;
-            if (ix && iy) dst[sn_pidx2(G, x + ix, y + iy, z + iz)] = v;
+            put(dst, x, y, z + iz);
+            if (ix) put(dst, x + ix, y, z + iz);
+            if (iy) put(dst, x, y + iy, z + iz);
+            if (ix && iy) put(dst, x + ix, y + iy, z + iz);
         }
     }
 }
 
-// canonical padded array <-> de-interleaved copy, every padded cell (ghosts included)
+// canonical padded array <-> split copy, every padded cell (ghosts included)
 __global__ void sn_convert_layout_kernel(float4 *__restrict__ lat, float4 *__restrict__ lat2, const SnGeom G, const int to_tiled)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G.rep_stride) return;
     const int zp = (int)(i % G.PZ), yp = (int)((i / G.PZ) % G.PY), xp = (int)(i / ((long long)G.PZ * G.PY));
     float4 *a = lat + (long long)blockIdx.y * G.rep_stride + i;
-    float4 *b = lat2 + (long long)blockIdx.y * sn_rep_stride2(G) + sn_pidx2(G, xp - G.g, yp - G.g, zp - G.gz);
-    if (to_tiled) *b = *a; else *a = *b;
+    float4 *b = lat2 + (long long)blockIdx.y * sn_rep_stride2(G);
+    const long long c = sn_pidx2(G, xp - G.g, yp - G.g, zp - G.gz);
+    if (to_tiled) sn_st2(b, G, c, *a); else *a = sn_ld2(b, G, c);
 }
 
 // Tile colours along one axis of n tiles: tiles that are active together must not be neighbours, also across the
@@ -300,6 +333,8 @@ struct SnTileFlow {
     unsigned int *err;                  // SN_FLAGS_ERR of this handle: raised when a dependency wait runs out of time
     unsigned long long timeout_ns;      // bound of one dependency wait
 };
+
+struct SnTileMaps { CUtensorMap xy, z, l; };     // tensor maps of the three arrays of the split copy
 
 struct __align__(16) SnTileItem {
     int x0, y0, z0, rep;                // tile origin (slab-local z) and replica
@@ -389,10 +424,12 @@ __device__ __forceinline__ void sn_tile_publish(const SnTileFlow &f, const SnTil
 // ordinal) for sn_mc_sweep_audit; the arithmetic and the order are those of the product instantiation.
 template <bool SPECIES, bool AUDIT>
 __global__ void __launch_bounds__(snt::THREADS, 1)
-sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, const SnTileFlow fl)
+sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, const SnTileFlow fl)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    float4 *tile = reinterpret_cast<float4 *>(smem);
+    float4 *tile_xy = reinterpret_cast<float4 *>(smem);                     // [22 * 22 columns][14 plane pairs] (x0, y0, x1, y1)
+    float2 *tile_z = reinterpret_cast<float2 *>(smem + snt::OFF_Z);         // ... (z0, z1)
+    float2 *tile_l = reinterpret_cast<float2 *>(smem + snt::OFF_L);         // ... (l0, l1), SPECIES only
     const uint32_t bar = sn_smem_u32(smem + snt::OFF_BAR);
     SnTileItem *ctl_item = reinterpret_cast<SnTileItem *>(smem + snt::OFF_CTL);
     unsigned int *ctl_wbread = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 48);   // worker warps that reached the write-back
@@ -407,10 +444,11 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     // load as soon as the workers have let go of the shared tile, and publishes the finished tile's version
     // once their stores have landed -- all the global-memory round trips of the scheduling stay off the
     // workers' critical path.
-    // thread -> (column i,j ; segment k of 4 z sites ; half h of the segment).  k and the low bit of j
-    // vary inside a quarter-warp, so its 8 lanes read 8 distinct 16-byte bank groups (28 j + k mod 8).
+    // thread -> (column i,j ; segment k of 4 z sites ; half h of the segment).  The plane pair of a thread's two
+    // sites is 2 + 2k + h: k and h are the low lane bits, so a quarter-warp reads 8 consecutive 16-byte (x,y) pairs
+    // and a half-warp (two columns 4 apart in y: 56 = 8 mod 16 pairs) 16 distinct 8-byte z pairs.
     const int tid = threadIdx.x, role = tid >> 7, tl = tid & 127, lane = tid & 31, i = tl >> 5;
-    const int k = lane & 3, h = (lane >> 3) & 1, j = ((lane >> 2) & 1) | ((lane >> 4) << 1);
+    const int k = lane & 3, h = (lane >> 2) & 1, j = lane >> 3;
     const bool ctrl = tid >= snt::WORKERS;
     float2 *xF = reinterpret_cast<float2 *>(smem + snt::OFF_XF);
     float4 *xP = reinterpret_cast<float4 *>(smem + snt::OFF_XP);
@@ -425,27 +463,23 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
     uint32_t parity = 0;
     const SnGeom &G = a.G;
 
-    // z part of the shared-memory index for plane (4k + 2h + e), e = -3..4
-    int zoff[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int w = 4 + 4 * k + 2 * h + (e - 3);          // plane index inside the 28-plane window
-        zoff[e] = (w & 3) * snt::BOX_STRIDE_F4 + (w >> 2);
-    }
+    const int pair0 = 2 + 2 * k + h;          // plane pair of the thread's two sites inside the 14 pairs of a column
 
-    // TMA load of a tile into shared memory (4 residue boxes), completion on the mbarrier (one thread)
+    // TMA load of a tile into shared memory (one box per array), completion on the mbarrier (one thread)
     auto issue_tile_load = [&](const SnTileItem &it) {
         // shared memory was last touched through the generic proxy; order it before the async-proxy writes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4 * snt::BOX_BYTES) : "memory");
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const uint32_t dst = sn_smem_u32(smem) + r * snt::BOX_STRIDE_F4 * 16;
-            // tensor = (floats of one residue run, run, padded y, padded x, replica); the window of a tile at
-            // z0 starts at position z0/4 of every run, i.e. float z0; halo x0-3 / y0-3 -> padded x0 / y0
-            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                         ::"r"(dst), "l"(&tmap), "r"(it.z0), "r"(r), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
-        }
+        constexpr int BYTES = snt::XY_BYTES + snt::Z_BYTES + (SPECIES ? snt::Z_BYTES : 0);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
+        // tensor = (floats of one z row, padded y, padded x, replica); the 28-plane window of a tile at z0 starts at
+        // row position z0 (plane z0 - 4); halo x0-3 / y0-3 -> padded x0 / y0
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(sn_smem_u32(smem)), "l"(&maps.xy), "r"(2 * it.z0), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                     ::"r"(sn_smem_u32(smem + snt::OFF_Z)), "l"(&maps.z), "r"(it.z0), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
+        if constexpr (SPECIES)
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                         ::"r"(sn_smem_u32(smem + snt::OFF_L)), "l"(&maps.l), "r"(it.z0), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
     };
     // Block-wide rendezvous of the control warp and the workers.  They meet from different places in the code, so this
     // is a named barrier with an explicit thread count (bar.sync 2, THREADS), not __syncthreads().
@@ -529,7 +563,7 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         { const float4 E = a.efield[rep]; tm.E = make_float3(E.x, E.y, E.z); tm.cage = E.w; }
         tm.constrain = a.constrain; tm.dim = a.dim;
         const uint4 rkey = a.rep_key[rep];
-        // a.lat / a.peer_* are the z-de-interleaved copies here (layout sn_pidx2)
+        // a.lat / a.peer_* are the split copies here (layout sn_pidx2)
         const long long rs2 = sn_rep_stride2(G);
         float4 *glat = a.lat + (long long)rep * rs2;
         float4 *plo = a.peer_lo ? a.peer_lo + (long long)rep * rs2 : nullptr;
@@ -561,16 +595,14 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
 
         // role B's share of the fields of super-pass sp, left in xF[sp & 1]
         auto gather_b = [&](int sp) {
-            const int colbase = ((snt::H + (sp >> 2) + 4 * i) * snt::BX + (snt::H + (sp & 3) + 4 * j)) * snt::NQ;
-            const float4 *pe[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) pe[e] = tile + colbase + zoff[e];
+            const int cell = ((snt::H + (sp >> 2) + 4 * i) * snt::BX + (snt::H + (sp & 3) + 4 * j)) * snt::NP + pair0;
+            const SnTileCol tc{tile_xy + cell, tile_z + cell, tile_l + cell};
             float3 F[2], Gc[2];
             float4 old[2];
 #ifdef SN_EXP_NOGB
-            sn_tile_gather2<0u, false, SPECIES>(pe, F, Gc, old);
+            sn_tile_gather2<0u, false, SPECIES>(tc, F, Gc, old);
 #else
-            sn_tile_gather2<snt::MASK_B, false, SPECIES>(pe, F, Gc, old);
+            sn_tile_gather2<snt::MASK_B, false, SPECIES>(tc, F, Gc, old);
 #endif
             float2 *dst = xF + (sp & 1) * 3 * snt::SITE_THREADS + tl;
             dst[0 * snt::SITE_THREADS] = make_float2(F[0].x, F[0].y);
@@ -586,16 +618,14 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
             if (role == 0) {
                 const int cx = sp >> 2, cy = sp & 3;
                 const int gx = x0 + cx + 4 * i, gy = y0 + cy + 4 * j, gz = z0 + 4 * k + 2 * h;
-                const int colbase = ((snt::H + cx + 4 * i) * snt::BX + (snt::H + cy + 4 * j)) * snt::NQ;
-                const float4 *pe[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) pe[e] = tile + colbase + zoff[e];
+                const int cell = ((snt::H + cx + 4 * i) * snt::BX + (snt::H + cy + 4 * j)) * snt::NP + pair0;
+                const SnTileCol tc{tile_xy + cell, tile_z + cell, tile_l + cell};
                 float3 F[2], Gc[2];
                 float4 old[2];
 #ifdef SN_EXP_NOGA
-                sn_tile_gather2<0u, true, SPECIES>(pe, F, Gc, old);
+                sn_tile_gather2<0u, true, SPECIES>(tc, F, Gc, old);
 #else
-                sn_tile_gather2<snt::MASK_A, true, SPECIES>(pe, F, Gc, old);
+                sn_tile_gather2<snt::MASK_A, true, SPECIES>(tc, F, Gc, old);
 #endif
                 {
                     const float2 *src = xF + (sp & 1) * 3 * snt::SITE_THREADS + tl;
@@ -655,15 +685,18 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
 #endif
                     const float3 dp = acc ? dpp[s] : make_float3(0.f, 0.f, 0.f);
 #ifndef SN_EXP_NOSTS
-                    if (acc) *const_cast<float4 *>(pe[3 + s]) = make_float4(np[s].x, np[s].y, np[s].z, old[s].w);
+                    if (acc) {
+                        reinterpret_cast<float2 *>(tile_xy)[2 * cell + s] = make_float2(np[s].x, np[s].y);
+                        reinterpret_cast<float *>(tile_z)[2 * cell + s] = np[s].z;
+                    }
 #endif
                     n_acc += acc; n_rej += (mine & !acc & !vac[s]); n_vac += (mine & vac[s]);
                     if constexpr (AUDIT) {
                         if (mine) sn_audit_write(fl.audit, G, rep, gx, gy, gz + s, np[s], ua[s], dE, acc, vac[s], (item.p * 16 + sp) * 4 + t4);
                     }
                     if (t4 < 3) {
-                        const int srcS = (lane & 23) | ((t4 >> 1) << 3);            // owner of step t4 in this segment
-                        const int srcU = (((lane & 23) + 1) & 31) | ((t4 >> 1) << 3);   // ... in the segment above (k + 1)
+                        const int srcS = (lane & 27) | ((t4 >> 1) << 2);            // owner of step t4 in this segment
+                        const int srcU = (((lane & 27) + 1) & 27) | ((t4 >> 1) << 2);   // ... in the segment above (k + 1; unused for k == 3)
 #ifdef SN_EXP_NOSHFL
                         dpS[t4] = dp; dpU[t4] = make_float3(dp.y, dp.z, dp.x); (void)srcS; (void)srcU;
 #else
@@ -691,31 +724,35 @@ sn_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const SnSweepArgs a, c
         }
         // Write the tile's 16^3 interior back: shared memory -> registers, then (once everybody has read) the
         // TMA load of the next tile is started and the registers are stored to global memory underneath it.
-        // 16 lanes cover one (x,y) row: 4 residue runs x 4 consecutive positions, i.e. four 64-byte pieces
-        // in the de-interleaved global layout.  Sites on a lattice / slab face also go to their ghost
-        // images (periodic copies, or the neighbouring GPU's ghost planes over NVLink).
+        // 8 lanes cover one (x,y) row of 16 planes: 128 contiguous bytes of the xy array, 64 of the z array.  Rows
+        // on a lattice / slab face also go to their ghost images (periodic copies, or the neighbouring GPU's ghost
+        // planes over NVLink).
         SnTileItem nxt;
         {
-            float4 wb[16];
-            const int rr = (tid >> 2) & 3, qq = tid & 3, lz = 4 * qq + rr, row0 = tid >> 4;
-            const int zo = rr * snt::BOX_STRIDE_F4 + qq + 1;              // plane z0 + lz: run rr, window position qq + 1
+            float4 wbx[8];
+            float2 wbz[8];
+            const int pr = tid & 7, row0 = tid >> 3;                       // plane pair z0 + 2 pr, 32 rows per pass
 #pragma unroll
-            for (int pss = 0; pss < 16; pss++) {
-                const int row = pss * 16 + row0, lx = row >> 4, ly = row & 15;
-                wb[pss] = tile[((lx + snt::H) * snt::BX + (ly + snt::H)) * snt::NQ + zo];
+            for (int pss = 0; pss < 8; pss++) {
+                const int row = pss * 32 + row0, lx = row >> 4, ly = row & 15;
+                const int cell = ((lx + snt::H) * snt::BX + (ly + snt::H)) * snt::NP + 2 + pr;
+                wbx[pss] = tile_xy[cell];
+                wbz[pss] = tile_z[cell];
             }
             __syncwarp();
             if (lane == 0) atomicAdd(ctl_wbread, 1u);     // tells the control warp to stop polling and come to the hand-over
             __syncwarp();
             cta_sync();                                   // hand-over: the control warp starts the next TMA load
             nxt = *ctl_item;
-            const long long gbase = sn_pidx2(G, x0, y0, z0 + lz);
-            const long long sy2 = 4LL * sn_q2(G), sx2 = sy2 * G.PY;
+            float4 *gxy = glat;                                                            // pairs of the xy array
+            float2 *gz2 = reinterpret_cast<float2 *>(reinterpret_cast<float *>(glat) + 2 * rs2);   // pairs of the z array
+            const long long gbase = sn_pidx2(G, x0, y0, z0 + 2 * pr) >> 1;
+            const long long sy2 = sn_pz2(G) >> 1, sx2 = sy2 * G.PY;
 #pragma unroll
-            for (int pss = 0; pss < 16; pss++) {
-                const int row = pss * 16 + row0, lx = row >> 4, ly = row & 15;
-                if (face_tile) sn_store_site2(glat, plo, phi, G, x0 + lx, y0 + ly, z0 + lz, wb[pss]);
-                else glat[gbase + lx * sx2 + ly * sy2] = wb[pss];
+            for (int pss = 0; pss < 8; pss++) {
+                const int row = pss * 32 + row0, lx = row >> 4, ly = row & 15;
+                if (face_tile) sn_store_pair2(glat, plo, phi, G, rs2, x0 + lx, y0 + ly, z0 + 2 * pr, wbx[pss], wbz[pss]);
+                else { gxy[gbase + lx * sx2 + ly * sy2] = wbx[pss]; gz2[gbase + lx * sx2 + ly * sy2] = wbz[pss]; }
             }
         }
         // Release the tile's stores to the control warp at CTA scope (the lanes' stores are ordered before lane
@@ -767,21 +804,27 @@ int sn_tiled_prepare(sn_handle *h)
     cudaDriverEntryPointQueryResult qr;
     SN_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qr));
     if (!enc || qr != cudaDriverEntryPointSuccess) return sn_fail(SN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    // the de-interleaved copy (layout sn_pidx2) and its tensor map:
-    // dims = (floats of one residue run, 4 runs, padded y, padded x, replica); one TMA row = 7 float4 = 112 B
-    const long long Q = sn_q2(G), rs2 = sn_rep_stride2(G);
+    // the split copy (layout sn_pidx2) and the tensor maps of its three arrays:
+    // dims = (floats of one z row, padded y, padded x, replica); one TMA row = 28 planes = 224 B (xy) / 112 B (z, lengths)
+    const long long rs2 = sn_rep_stride2(G);
+    const int PZ2 = sn_pz2(G);
     const size_t bytes2 = (size_t)rs2 * h->p.nreplicas * sizeof(float4);
     if (cudaMalloc(&h->lat2, bytes2) != cudaSuccess) { cudaGetLastError(); return sn_fail(SN_ERR_NOMEM, "sn_create: cannot allocate %.1f MB for the tiled copy", bytes2 / 1e6); }
     SN_CUDA_CHECK(cudaMemsetAsync(h->lat2, 0, bytes2, h->stream));
     h->lat2_valid = false;
-    CUtensorMap *tm = new CUtensorMap;
-    const cuuint64_t gdim[5] = {(cuuint64_t)Q * 4, 4, (cuuint64_t)G.PY, (cuuint64_t)(G.X + 2 * G.g), (cuuint64_t)h->p.nreplicas};
-    const cuuint64_t gstr[4] = {(cuuint64_t)Q * 16, (cuuint64_t)Q * 64, (cuuint64_t)Q * 64 * G.PY, (cuuint64_t)rs2 * 16};
-    const cuuint32_t box[5] = {4 * snt::NQ, 1, snt::BX, snt::BX, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, h->lat2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { delete tm; return sn_fail(SN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); }
+    SnTileMaps *tm = new SnTileMaps;
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int which = 0; which < 3; which++) {
+        const int fpc = which == 0 ? 2 : 1;                           // floats per cell in this array
+        float *base = reinterpret_cast<float *>(h->lat2) + (which == 0 ? 0 : which == 1 ? 2 * rs2 : 3 * rs2);
+        const cuuint64_t gdim[4] = {(cuuint64_t)PZ2 * fpc, (cuuint64_t)G.PY, (cuuint64_t)(G.X + 2 * G.g), (cuuint64_t)h->p.nreplicas};
+        const cuuint64_t gstr[3] = {(cuuint64_t)PZ2 * fpc * 4, (cuuint64_t)PZ2 * fpc * 4 * G.PY, (cuuint64_t)rs2 * 16};
+        const cuuint32_t box[4] = {(cuuint32_t)(2 * snt::NP * fpc), snt::BX, snt::BX, 1};
+        CUtensorMap *m = which == 0 ? &tm->xy : which == 1 ? &tm->z : &tm->l;
+        const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete tm; return sn_fail(SN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); }
+    }
     h->tmap = tm;
     SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
     SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
@@ -792,7 +835,7 @@ int sn_tiled_prepare(sn_handle *h)
 
 void sn_tiled_release(sn_handle *h)
 {
-    delete reinterpret_cast<CUtensorMap *>(h->tmap);
+    delete reinterpret_cast<SnTileMaps *>(h->tmap);
     h->tmap = nullptr;
     cudaFree(h->lat2);
     h->lat2 = nullptr;
@@ -822,7 +865,7 @@ static int sn_slab_phase_sync(sn_handle *h, long long *launches);
 int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
 {
     const SnGeom &G = h->G;
-    const CUtensorMap &tm = *reinterpret_cast<const CUtensorMap *>(h->tmap);
+    const SnTileMaps &tm = *reinterpret_cast<const SnTileMaps *>(h->tmap);
     if (nsweeps <= 0) return SN_OK;
     if (!h->lat2_valid) {                            // first tiled sweep after the canonical array changed
         int rc = sn_sync_canonical(h);
@@ -834,7 +877,7 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
     if (!G.periodic_z) { int rc = sn_slab_phase_sync(h, launches); if (rc) return rc; }
 
     SnSweepArgs a = sn_sweep_args(h);
-    a.lat = h->lat2;                                  // the kernel works on the de-interleaved copies (own and neighbours')
+    a.lat = h->lat2;                                  // the kernel works on the split copies (own and neighbours')
     SnTileFlow f;
     f.tnx = G.X / snt::T; f.tny = G.Y / snt::T; f.tnz = G.nz / snt::T; f.nrep = h->p.nreplicas;
     f.ncx = sn_tc_ncol(f.tnx); f.ncy = sn_tc_ncol(f.tny); f.ncz = sn_tc_ncol(f.tnz); f.np = f.ncx * f.ncy * f.ncz;
