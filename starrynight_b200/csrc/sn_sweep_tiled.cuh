@@ -60,6 +60,10 @@
 #include "sn_field.cuh"
 #include "sn_sweep_colour.cuh"
 
+#ifndef SN_CTRL_POLL_NS
+#define SN_CTRL_POLL_NS 400             // pause between two looks at an unmet dependency (a tile takes ~27 us)
+#endif
+
 namespace snt {
 constexpr int T = 16;                    // tile edge
 constexpr int H = 3;                     // halo = cut-off
@@ -83,7 +87,10 @@ constexpr int THREADS = WORKERS + 32;      // + the control warp
 // chain, so it may not read a column of the class A is updating: seen from the next class (cx,cy+1)
 // those are the columns (0,-1), (0,3), and (-1,-1) when cx advances, i.e. pairs 0, 2 and 6.  Pairs 0 and
 // 5 are the in-plane cage-strain neighbours, kept with A so that B hands over dipole fields only.
-constexpr unsigned MASK_A = (1u << 0) | (1u << 2) | (1u << 5) | (1u << 6);
+#ifndef SN_MASK_A_EXTRA
+#define SN_MASK_A_EXTRA 0u              // further column pairs moved from role B to role A (balance experiments)
+#endif
+constexpr unsigned MASK_A = (1u << 0) | (1u << 2) | (1u << 5) | (1u << 6) | (SN_MASK_A_EXTRA);
 constexpr unsigned MASK_B = ((1u << NCOL) - 1u) & ~MASK_A;
 
 __host__ __device__ constexpr int half_height(int r2xy) { return 9 - r2xy >= 9 ? 3 : 9 - r2xy >= 4 ? 2 : 9 - r2xy >= 1 ? 1 : 0; }
@@ -101,32 +108,70 @@ __device__ __forceinline__ void sn_mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
-// Field accumulators of one site, kept as 9 independent FFMA chains (one per tensor entry)
-// so that a single warp per scheduler still has enough independent work in flight.
-struct SnAcc {
-    float xx, xy, xz, yx, yy, yz, zx, zy, zz;   // F.x = xx + xy + xz, ...
-    float gx, gy, gz;                           // cage-strain sum
+// Field accumulators of the thread's two sites: nine independent partial sums per site (one per tensor entry),
+// all held as register pairs so that the arithmetic is issued as packed FP32 instructions (Blackwell FADD2 /
+// FFMA2: two IEEE FP32 operations per issue slot, each half rounded exactly like the scalar FADD / FFMA, so the
+// chain is bit-identical to the scalar instruction stream).  The (x, y) half of a neighbour's moment pairs up
+// inside a site; the z half pairs up across the two sites, which see the same tensor T(dx,dy,dz) one plane
+// apart.  The kernel is bound by issue slots and shared-memory wavefronts, not by the FMA pipe: a full tensor
+// applied to both sites takes 12-13 slots instead of 24.
+struct SnAcc2 {
+    float2 d[2];                                // per site (xx, yy):  F.x += Txx ax,  F.y += Tyy ay
+    float2 o[2];                                // per site (yx, xy):  F.y += Txy ax,  F.x += Txy ay
+    float2 r[2];                                // per site (zx, zy):  F.z += Txz ax,  F.z += Tyz ay
+    float2 xz, yz, zz;                          // (site 0, site 1):   F.x += Txz az, F.y += Tyz az, F.z += Tzz az
+    float2 gxy[2], gz;                          // cage-strain sum: (gx, gy) per site, gz of (site 0, site 1)
 };
 
-// One neighbour pair r = (DX,DY,DZ) and -r: T(r) = T(-r), so the two moments are
-// added first and the tensor applied once (12 instead of 18 FP ops for a full tensor).
-template <int DX, int DY, int DZ, bool SPECIES>
-__device__ __forceinline__ void sn_accumulate_pair(SnAcc &A, const float4 a, const float4 b)
+#ifdef SN_NO_PACKED_FP32      // scalar instruction stream (same arithmetic), kept for A/B timing
+__device__ __forceinline__ float2 sn_add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 sn_fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
+__device__ __forceinline__ float2 sn_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sn_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+
+// One neighbour pair r = (DX,DY,DZ) and -r for both sites of the thread (site 1 lies one plane above site 0, so
+// its neighbours a1 / b1 are the planes after a0 / b0).  T(r) = T(-r): the two moments are added first and the
+// tensor applied once.  ZPAIR: (a0.z, a1.z) and (b0.z, b1.z) are register pairs as loaded (one LDS.64 each),
+// so their sum is one FADD2; otherwise two FADDs write the halves of the pair.
+template <int DX, int DY, int DZ, bool SPECIES, bool ZPAIR>
+__device__ __forceinline__ void sn_accumulate_pair2(SnAcc2 &A, const float4 a0, const float4 b0, const float4 a1, const float4 b1)
 {
     constexpr float txx = sn_T(DX, DY, DZ, 0, 0), tyy = sn_T(DX, DY, DZ, 1, 1), tzz = sn_T(DX, DY, DZ, 2, 2);
     constexpr float txy = sn_T(DX, DY, DZ, 0, 1), txz = sn_T(DX, DY, DZ, 0, 2), tyz = sn_T(DX, DY, DZ, 1, 2);
-    float ax, ay, az;
-    if constexpr (SPECIES) { ax = fmaf(a.x, a.w, b.x * b.w); ay = fmaf(a.y, a.w, b.y * b.w); az = fmaf(a.z, a.w, b.z * b.w); }
-    else { ax = a.x + b.x; ay = a.y + b.y; az = a.z + b.z; }
-    if constexpr (txx != 0.0f) A.xx = fmaf(txx, ax, A.xx);
-    if constexpr (tyy != 0.0f) A.yy = fmaf(tyy, ay, A.yy);
-    if constexpr (tzz != 0.0f) A.zz = fmaf(tzz, az, A.zz);
-    if constexpr (txy != 0.0f) { A.xy = fmaf(txy, ay, A.xy); A.yx = fmaf(txy, ax, A.yx); }
-    if constexpr (txz != 0.0f) { A.xz = fmaf(txz, az, A.xz); A.zx = fmaf(txz, ax, A.zx); }
-    if constexpr (tyz != 0.0f) { A.yz = fmaf(tyz, az, A.yz); A.zy = fmaf(tyz, ay, A.zy); }
+    float2 axy[2], az;
+    if constexpr (SPECIES) {
+        axy[0] = make_float2(fmaf(a0.x, a0.w, b0.x * b0.w), fmaf(a0.y, a0.w, b0.y * b0.w));
+        axy[1] = make_float2(fmaf(a1.x, a1.w, b1.x * b1.w), fmaf(a1.y, a1.w, b1.y * b1.w));
+        az = make_float2(fmaf(a0.z, a0.w, b0.z * b0.w), fmaf(a1.z, a1.w, b1.z * b1.w));
+    } else {
+        axy[0] = sn_add2(make_float2(a0.x, a0.y), make_float2(b0.x, b0.y));
+        axy[1] = sn_add2(make_float2(a1.x, a1.y), make_float2(b1.x, b1.y));
+        if constexpr (ZPAIR) az = sn_add2(make_float2(a0.z, a1.z), make_float2(b0.z, b1.z));
+        else az = make_float2(a0.z + b0.z, a1.z + b1.z);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        if constexpr (txx != 0.0f && tyy != 0.0f) A.d[s] = sn_fma2(make_float2(txx, tyy), axy[s], A.d[s]);
+        else if constexpr (txx != 0.0f) A.d[s].x = fmaf(txx, axy[s].x, A.d[s].x);
+        else if constexpr (tyy != 0.0f) A.d[s].y = fmaf(tyy, axy[s].y, A.d[s].y);
+        if constexpr (txy != 0.0f) A.o[s] = sn_fma2(make_float2(txy, txy), axy[s], A.o[s]);
+        if constexpr (txz != 0.0f && tyz != 0.0f) A.r[s] = sn_fma2(make_float2(txz, tyz), axy[s], A.r[s]);
+        else if constexpr (txz != 0.0f) A.r[s].x = fmaf(txz, axy[s].x, A.r[s].x);
+        else if constexpr (tyz != 0.0f) A.r[s].y = fmaf(tyz, axy[s].y, A.r[s].y);
+    }
+    if constexpr (tzz != 0.0f) A.zz = sn_fma2(make_float2(tzz, tzz), az, A.zz);
+    if constexpr (txz != 0.0f) A.xz = sn_fma2(make_float2(txz, txz), az, A.xz);
+    if constexpr (tyz != 0.0f) A.yz = sn_fma2(make_float2(tyz, tyz), az, A.yz);
     if constexpr (DX * DX + DY * DY + DZ * DZ == 1) {
-        if constexpr (SPECIES) { A.gx += a.x + b.x; A.gy += a.y + b.y; A.gz += a.z + b.z; }
-        else { A.gx += ax; A.gy += ay; A.gz += az; }
+        if constexpr (SPECIES) {
+            A.gxy[0] = sn_add2(A.gxy[0], sn_add2(make_float2(a0.x, a0.y), make_float2(b0.x, b0.y)));
+            A.gxy[1] = sn_add2(A.gxy[1], sn_add2(make_float2(a1.x, a1.y), make_float2(b1.x, b1.y)));
+            A.gz = sn_add2(A.gz, make_float2(a0.z + b0.z, a1.z + b1.z));
+        } else {
+            A.gxy[0] = sn_add2(A.gxy[0], axy[0]); A.gxy[1] = sn_add2(A.gxy[1], axy[1]); A.gz = sn_add2(A.gz, az);
+        }
     }
 }
 
@@ -187,19 +232,21 @@ __device__ __forceinline__ void sn_tile_load_pair(const SnTileCol &tc, float4 (&
 }
 
 template <int IDX, bool SPECIES>
-__device__ __forceinline__ void sn_tile_compute_pair(const float4 (&wp)[6], const float4 (&wm)[6], SnAcc (&A)[2])
+__device__ __forceinline__ void sn_tile_compute_pair(const float4 (&wp)[6], const float4 (&wm)[6], SnAcc2 &A)
 {
     constexpr snt::Col c = snt::col(IDX);
     constexpr int M = snt::half_height(c.dx * c.dx + c.dy * c.dy);
-    sn_static_for<0, 2>([&](auto sc) {
-        sn_static_for<-M, M + 1>([&](auto dzc) {
-            constexpr int S = decltype(sc)::value, DZ = decltype(dzc)::value;
+    // site S sees plane e of a column at window index e + M; w[M + 2t], w[M + 2t + 1] come from one plane pair
+    sn_static_for<-M, M + 1>([&](auto dzc) {
+        constexpr int DZ = decltype(dzc)::value;
 #ifdef SN_EXP_NOFP        // experiment: loads only, one add per loaded word
-            if constexpr (DZ == 0 || (S == 0 && DZ < 0) || (S == 1 && DZ > 0)) { A[S].xx += wp[S + DZ + M].x; A[S].yy += wm[S - DZ + M].y; }
-#else
-            sn_accumulate_pair<c.dx, c.dy, DZ, SPECIES>(A[S], wp[S + DZ + M], wm[S - DZ + M]);
-#endif
+        sn_static_for<0, 2>([&](auto sc) {
+            constexpr int S = decltype(sc)::value;
+            if constexpr (DZ == 0 || (S == 0 && DZ < 0) || (S == 1 && DZ > 0)) { A.d[S].x += wp[S + DZ + M].x; A.d[S].y += wm[S - DZ + M].y; }
         });
+#else
+        sn_accumulate_pair2<c.dx, c.dy, DZ, SPECIES, (DZ % 2 == 0)>(A, wp[DZ + M], wm[M - DZ], wp[1 + DZ + M], wm[1 - DZ + M]);
+#endif
     });
 }
 
@@ -213,7 +260,7 @@ __host__ __device__ constexpr int next_in(unsigned mask, int idx)
 }  // namespace snt
 
 template <unsigned MASK, int IDX, bool SPECIES>
-__device__ __forceinline__ void sn_tile_gather_chain(const SnTileCol &tc, SnAcc (&A)[2], float4 (&c0)[6], float4 (&c1)[6])
+__device__ __forceinline__ void sn_tile_gather_chain(const SnTileCol &tc, SnAcc2 &A, float4 (&c0)[6], float4 (&c1)[6])
 {
     // c0/c1 hold pair IDX (already loaded); load the next pair of the mask, then do the arithmetic of this one
     if constexpr (IDX < snt::NCOL) {
@@ -225,6 +272,20 @@ __device__ __forceinline__ void sn_tile_gather_chain(const SnTileCol &tc, SnAcc 
     }
 }
 
+// Same, with the loads running two column pairs ahead of the arithmetic (SN_EXP_DEPTH2)
+template <unsigned MASK, int IDX, bool SPECIES>
+__device__ __forceinline__ void sn_tile_gather_chain2(const SnTileCol &tc, SnAcc2 &A, float4 (&c0)[6], float4 (&c1)[6], float4 (&n0)[6], float4 (&n1)[6])
+{
+    if constexpr (IDX < snt::NCOL) {
+        constexpr int N1 = snt::next_in(MASK, IDX + 1);
+        constexpr int N2 = N1 < snt::NCOL ? snt::next_in(MASK, N1 + 1) : snt::NCOL;
+        float4 m0[6], m1[6];
+        if constexpr (N2 < snt::NCOL) sn_tile_load_pair<N2, SPECIES>(tc, m0, m1);
+        sn_tile_compute_pair<IDX, SPECIES>(c0, c1, A);
+        if constexpr (N1 < snt::NCOL) sn_tile_gather_chain2<MASK, N1, SPECIES>(tc, A, n0, n1, m0, m1);
+    }
+}
+
 // Contribution of the column pairs in MASK -- and of the thread's own column when CENTRE -- to
 // the local fields of the thread's 2 consecutive z sites.  tc points at the plane pair of the thread's
 // own two sites; a neighbour column is a compile-time immediate away.  Each
@@ -233,14 +294,22 @@ __device__ __forceinline__ void sn_tile_gather_chain(const SnTileCol &tc, SnAcc 
 template <unsigned MASK, bool CENTRE, bool SPECIES>
 __device__ __forceinline__ void sn_tile_gather2(const SnTileCol &tc, float3 (&F)[2], float3 (&G)[2], float4 (&old)[2])
 {
-    SnAcc A[2];
+    SnAcc2 A;
 #pragma unroll
-    for (int s = 0; s < 2; s++) A[s] = SnAcc{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < 2; s++) A.d[s] = A.o[s] = A.r[s] = A.gxy[s] = make_float2(0.f, 0.f);
+    A.xz = A.yz = A.zz = A.gz = make_float2(0.f, 0.f);
     constexpr int FIRST = snt::next_in(MASK, 0);
     if constexpr (FIRST < snt::NCOL) {
         float4 c0[6], c1[6];
         sn_tile_load_pair<FIRST, SPECIES>(tc, c0, c1);
+#ifdef SN_EXP_DEPTH2
+        constexpr int SECOND = snt::next_in(MASK, FIRST + 1);
+        float4 n0[6], n1[6];
+        if constexpr (SECOND < snt::NCOL) sn_tile_load_pair<SECOND, SPECIES>(tc, n0, n1);
+        sn_tile_gather_chain2<MASK, FIRST, SPECIES>(tc, A, c0, c1, n0, n1);
+#else
         sn_tile_gather_chain<MASK, FIRST, SPECIES>(tc, A, c0, c1);
+#endif
     }
     if constexpr (CENTRE) {
         // own column: pairs (0,0,+-dz); also yields the current values of the 2 sites
@@ -248,17 +317,15 @@ __device__ __forceinline__ void sn_tile_gather2(const SnTileCol &tc, float3 (&F)
         sn_tile_load_col<0, 3, SPECIES>(tc, w);
         const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], w6 = w[6], w7 = w[7];
         old[0] = w3; old[1] = w4;
-        sn_accumulate_pair<0, 0, 1, SPECIES>(A[0], w4, w2);
-        sn_accumulate_pair<0, 0, 2, SPECIES>(A[0], w5, w1);
-        sn_accumulate_pair<0, 0, 3, SPECIES>(A[0], w6, w0);
-        sn_accumulate_pair<0, 0, 1, SPECIES>(A[1], w5, w3);
-        sn_accumulate_pair<0, 0, 2, SPECIES>(A[1], w6, w2);
-        sn_accumulate_pair<0, 0, 3, SPECIES>(A[1], w7, w1);
+        sn_accumulate_pair2<0, 0, 1, SPECIES, false>(A, w4, w2, w5, w3);
+        sn_accumulate_pair2<0, 0, 2, SPECIES, true>(A, w5, w1, w6, w2);
+        sn_accumulate_pair2<0, 0, 3, SPECIES, false>(A, w6, w0, w7, w1);
     }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        F[s] = make_float3(A[s].xx + A[s].xy + A[s].xz, A[s].yx + A[s].yy + A[s].yz, A[s].zx + A[s].zy + A[s].zz);
-        G[s] = make_float3(A[s].gx, A[s].gy, A[s].gz);
+        const float xz = s ? A.xz.y : A.xz.x, yz = s ? A.yz.y : A.yz.x, zz = s ? A.zz.y : A.zz.x;
+        F[s] = make_float3(A.d[s].x + A.o[s].y + xz, A.o[s].x + A.d[s].y + yz, A.r[s].x + A.r[s].y + zz);
+        G[s] = make_float3(A.gxy[s].x, A.gxy[s].y, s ? A.gz.y : A.gz.x);
     }
 }
 
@@ -525,11 +592,16 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
         for (unsigned int done = 8; cur.valid; done += 8) {
             // while the workers compute `cur`: next item, first look at its dependencies
             SnTileItem nxt = take();
-            bool ready = false;
-            while (*reinterpret_cast<volatile unsigned int *>(ctl_wbread) + 8u - done == 0u) {     // no worker warp at the write-back yet
-                if (nxt.valid && !ready) ready = sn_tile_deps_ready(fl, nxt, lane);
-                else __nanosleep(100);
+            // Poll only while the next item's dependencies are unmet and no worker warp has reached the write-back, with a
+            // pause between looks: the control warp shares its scheduler with two worker warps, and every instruction it
+            // issues is a slot they do not get (the v11 profile had 19 % of all executed instructions in this loop).  Once
+            // the dependencies are met it blocks in the hand-over barrier, which costs nothing.
+            bool ready = !nxt.valid;
+            while (!ready && *reinterpret_cast<volatile unsigned int *>(ctl_wbread) + 8u - done == 0u) {
+                ready = sn_tile_deps_ready(fl, nxt, lane);
+                if (!ready) __nanosleep(SN_CTRL_POLL_NS);
             }
+            ready = ready && nxt.valid;
             if (ready) deps_met();
             nxt.ready = ready;
             if (lane == 0) *ctl_item = nxt;
@@ -574,7 +646,7 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
         // (global site of the first one, replica, sweep): per site 64 random bits = 32 (accept) + 20 + 20, the low 8
         // bits of the accept word doubling as the last bits of the azimuth (they only reach the accept uniform
         // when it is below 2^-8, as resolution beyond 2^-24).
-        auto draw = [&](int sp) {
+        auto draw = [&](int sp) __attribute__((always_inline)) {
             const int gx = x0 + (sp >> 2) + 4 * i, gy = y0 + (sp & 3) + 4 * j, gz = z0 + 4 * k + 2 * h;
             const unsigned long long gsite = ((unsigned long long)gx * G.Y + gy) * G.Z + (G.z0 + gz);
             const Philox4 r = sn_philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32) ^ rkey.z, sweep_lo, sweep_hi, rkey.x, rkey.y);
@@ -594,7 +666,7 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
         parity ^= 1;
 
         // role B's share of the fields of super-pass sp, left in xF[sp & 1]
-        auto gather_b = [&](int sp) {
+        auto gather_b = [&](int sp) __attribute__((always_inline)) {
             const int cell = ((snt::H + (sp >> 2) + 4 * i) * snt::BX + (snt::H + (sp & 3) + 4 * j)) * snt::NP + pair0;
             const SnTileCol tc{tile_xy + cell, tile_z + cell, tile_l + cell};
             float3 F[2], Gc[2];
@@ -717,8 +789,15 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
                 }
             } else if (sp < 15) {
                 // one super-pass ahead of the chain: none of role B's columns belongs to the class being updated
+                // Role B draws first and gathers second, role A gathers first and runs the chain second: the two roles'
+                // shared-memory phases alternate instead of colliding at the start of the super-pass (+13 % at 512^3).
+#ifdef SN_EXP_GATHER_FIRST
                 gather_b(sp + 1);
                 draw(sp + 1);
+#else
+                draw(sp + 1);
+                gather_b(sp + 1);
+#endif
             }
             workers_sync();
         }
