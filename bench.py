@@ -10,7 +10,8 @@ random start.  One "step" = SWEEPS_PER_STEP full-lattice sweeps (one attempt at
 every site per sweep).  At N > 1 the same lattice is Z-slab decomposed (strong
 scaling), halo planes pushed GPU-to-GPU over NVLink by the sweep kernel itself.
 ``--workload c2|c3|c4|c5b`` measures the other BASELINE configurations through the
-same contract (see WORKLOADS); the default line is unchanged.
+same contract (see WORKLOADS); ``--workload obs`` measures one analysis pass (the observables of
+analysis_midpoint) in sites/s; the default line is unchanged.
 
   value  whole-job attempts/s with the lattice resident in HBM (CUDA events on the
          library's own stream, max over ranks)
@@ -73,6 +74,9 @@ WORKLOADS = {
     "c3": dict(what="64^3 lattice, DipoleCutOff=3, T = 0..500 K step 25 x CageStrain {0,1,2} = 63 replicas, one launch "
                     "(BASELINE.json configs[2]; the reference's `superparallel` grid, Makefile:52-54)",
                shape=(64, 64, 64), replicas=63, slabs=False, sweeps=40, temps=list(range(0, 501, 25)), cages=(0.0, 1.0, 2.0)),
+    "obs": dict(what="one analysis pass (analysis_midpoint, main.c:51-96: recombination_calculator + radial_order_parameter + lattice_Efield + "
+                     "potential map, plus polarisation / Landau order) over a resident 256^3 lattice, DipoleCutOff=3, after 2 sweeps at T=300 K",
+                shape=(256, 256, 256), replicas=1, slabs=True, sweeps=2, analysis=True),
     "c4": dict(what="128^3 MA/FA solid solution: Dipoles=[1.0,0.5,0.0] Prevalence=[0.6,0.3,0.1] (two species + vacancies), triangular Efield.x "
                     "ramp +-0.1 in 64 points, 1 sweep per point, 8 independent loops (seeds) (BASELINE.json configs[3])",
                shape=(128, 128, 128), replicas=8, slabs=True, sweeps=64, species=((1.0, 0.5, 0.0), (0.6, 0.3, 0.1)), ramp=(0.1, 64)),
@@ -585,6 +589,164 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- analysis workload
+RDF_OFFSETS, POT_OFFSETS, EF_OFFSETS = 2969, 924, 256      # lattice vectors with r^2 <= 80 / 0 < d <= 6 / 0 < d <= 4 (analysis.c:540, 68, 397)
+RDF_FLOP_PER_PAIR = 22.0     # FE dot 5 + two n.p dots 10 + AFE combine 3 + two histogram adds 2 + the products with n 2 (analysis.c:566-578)
+
+
+def _analysis_cpu(shape, seed):
+    """The reference's own analysis routines (oracle/_ref) on a small lattice: seconds per site of each."""
+    from oracle import oracle_api as oa
+    import tempfile
+    X, Y, Z = shape
+    p = oa.make_params(X, Y, Z, 3, 1.0, 0.0, (0.0, 0.0, 0.0), 1.0, 0, 3, T_KELVIN)
+    use_ref = oa.ref_available("f32")
+    lat = oa.random_lattice(X, Y, Z, seed=seed)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        if use_ref:
+            r = oa.RefLib("f32"); r.configure(p); r.set_lattice(lat)
+            calls = {"rdf": lambda: r.rdf_file(os.path.join(d, "rdf.dat")), "potential": r.potential_map,
+                     "efield": lambda: r.efield_map(4, False), "recombination": lambda: r.recombination_log(os.path.join(d, "rec.log"))}
+        else:
+            o = oa.Oracle("f32")
+            calls = {"rdf": lambda: o.rdf(p, lat), "potential": lambda: o.potential_map(p, lat),
+                     "efield": lambda: o.efield_map(p, lat, 4, False), "recombination": lambda: o.recombination(p, lat)}
+        for k, f in calls.items():
+            t0 = time.perf_counter(); f(); out[k] = time.perf_counter() - t0
+    return out, ("reference" if use_ref else "port")
+
+
+def run_analysis(args):
+    """--workload obs: sites per second through one analysis pass.  value: lattice resident in HBM, maps left to the
+    caller in pinned host memory (the pass the driver runs every mega-step); e2e: the same pass including the upload of
+    the lattice from pinned host memory.  Z-slabs at N > 1: every rank analyses its own slab (neighbour planes are read
+    over NVLink by the kernels), the histogram / partition sums are merged with one small all_reduce."""
+    import torch
+    import torch.distributed as dist
+    import starrynight_b200 as sn
+    from starrynight_b200 import slab as sn_slab
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    n = world
+    w = args.w
+    X, Y, Z = w["shape"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t_all = time.perf_counter()
+        edge = 40
+        secs, kind = _analysis_cpu((edge, edge, edge), 5)
+        for _ in range(max(0, args.warmup + args.steps - 1)):
+            secs, kind = _analysis_cpu((edge, edge, edge), 5)
+        tot = sum(secs.values())
+        v = edge ** 3 / tot
+        cfg = workload_config(args, 1); cfg["reference_step"] = {"sites": edge ** 3, "seconds": secs}
+        print(json.dumps({"metric": "analysis_sites_per_s", "value": v, "unit": "sites/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * tot, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "sites/s", "cores": 1, "kind": kind,
+                                           "sample": f"the reference's serial analysis routines on a {edge}^3 random lattice (cost per site does not depend on the size)"},
+                          "e2e": {"value": v, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+                          "wall_s": time.perf_counter() - t_all}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    if n > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if n > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nz = Z // n; z0 = rank * nz
+    host = synthetic_slab(w["shape"], z0, nz, seed=1234)
+    sim = sn.Simulation(X, Y, Z, DipoleCutOff=3, CageStrain=1.0, beta=sn.beta_of_T(T_KELVIN), seed=0xDEADBEEF + T_KELVIN, device=local,
+                        z0=z0 if n > 1 else 0, nz=nz if n > 1 else 0)
+    if n > 1:
+        sn_slab.wire_ipc(sim, dist, n, rank)
+    sim.set_lattice_ptr(host.data_ptr(), 0)
+    sim.pull_ghosts()
+    sim.MC_sweeps(w["sweeps"])
+    sim.synchronize()
+    nsl = X * Y * nz
+    vmap = torch.empty(nsl, dtype=torch.float64).pin_memory().numpy()
+    emap = torch.empty(nsl, dtype=torch.float64).pin_memory().numpy()
+    parts = {}
+
+    def timed(name, f, *a, **k):
+        t0 = time.perf_counter(); r = f(*a, **k); parts[name] = parts.get(name, 0.0) + time.perf_counter() - t0
+        return r
+
+    def one_pass():
+        res = {}
+        res["P"] = timed("polarisation", sim.polarisation)
+        res["landau"] = timed("landau_order", sim.landau_order)
+        res["rec"] = timed("recombination", sim.recombination_partial)
+        res["rdf"] = timed("rdf", sim.radial_order_parameter)
+        timed("efield_map", sim.dipole_electricfield, 4, False, 0, emap)
+        timed("potential_map", sim.dipole_potential, 0, vmap)
+        if n > 1:                                     # the one collective of the pass: histogram and partition sums
+            t = torch.from_numpy(np.concatenate([res["rdf"][0], res["rdf"][1], np.asarray(res["rec"], np.float64)[:5]])).cuda()
+            dist.all_reduce(t)
+            res["merged"] = t.cpu().numpy()
+        return res
+
+    for _ in range(args.warmup):
+        one_pass()
+    parts.clear()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = one_pass()
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: the lattice comes from pinned host memory every step
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.set_lattice_ptr(host.data_ptr(), 0)
+        sim.pull_ghosts()
+        one_pass_res = one_pass()
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    if n > 1:
+        t = torch.tensor([dt, dt_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt, dt_e2e = [float(v) for v in t.tolist()]
+    if rank == 0:
+        sites = X * Y * Z
+        rdf_ms = 1e3 * parts["rdf"] / (2 * args.steps)              # both loops ran it
+        fp64_peak = sim.fp64_peak_tflops()
+        ach = RDF_FLOP_PER_PAIR * RDF_OFFSETS * nsl / (rdf_ms * 1e-3) / 1e12
+        fe, afe, cnt = res["rdf"]
+        line = {"metric": "analysis_sites_per_s", "value": sites * args.steps / dt, "unit": "sites/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, n),
+                "e2e": {"value": sites * args.steps / dt_e2e, "unit": "sites/s", "h2d_bytes_per_step": sites * 16, "d2h_bytes_per_step": 2 * sites * 8 + 8 * (2 * 81 + 20),
+                        "mode": "lattice uploaded from pinned host memory every step; potential and |E| maps downloaded to pinned host memory"},
+                "gpu_launches": 9 * args.steps, "clocks": clocks,
+                "parts_ms": {k: 1e3 * v / (2 * args.steps) for k, v in parts.items()},
+                "roofline": {"bound": "fp64", "kernel": "sn_rdf_tiled_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
+                             "basis": "ALGORITHMIC flops of radial_order_parameter: %d pair terms per site x %d flop (analysis.c:566-578); the kernel walks one of every +-d pair" % (RDF_OFFSETS, int(RDF_FLOP_PER_PAIR)),
+                             "peak_source": "DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)", "avg_launch_ms": rdf_ms, "traffic": None},
+                "rdf_nearest_shell": {"fe": float(fe[1] / cnt[1]), "afe": float(afe[1] / cnt[1])}}
+        if n == 1 and not args.no_cpu_baseline:
+            try:
+                secs, kind = _analysis_cpu((40, 40, 40), 5)
+                line["cpu_baseline"] = {"value": 40 ** 3 / sum(secs.values()), "unit": "sites/s", "cores": 1, "kind": kind,
+                                        "sample": "the reference's serial analysis routines (rdf %.2f s, potential %.2f s, efield %.2f s, recombination %.2f s) on a 40^3 random lattice"
+                                                  % (secs["rdf"], secs["potential"], secs["efield"], secs["recombination"])}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "sites/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if n > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def executed_roofline(kernel, attempts_per_launch, avg_launch_ms, peak_tf):
     """Pipe-level view beside the algorithmic roofline: FP32 instructions the kernel really executes per attempt
     (ncu inst_executed_pipe_fma of the committed capture, profiles/traffic.json), each counted as one FMA = 2 flop."""
@@ -602,7 +764,9 @@ def executed_roofline(kernel, attempts_per_launch, avg_launch_ms, peak_tf):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.w.get("analysis"):
+        run_analysis(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

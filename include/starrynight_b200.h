@@ -230,6 +230,8 @@ SN_API int sn_philox_kat(int n, const unsigned int *counter_key, unsigned int *o
 /* measurement aid for bench.py: sustained FFMA throughput of `device` in TFLOP/s, the
  * denominator of the FP32 CUDA-core roofline (MEASURED_PEAKS.json carries no FP32 figure) */
 SN_API int sn_bench_fp32_peak(int device, double *tflops);
+/* the same for DFMA: the denominator of the FP64 roofline of the observable kernels (analysis.c sums in double) */
+SN_API int sn_bench_fp64_peak(int device, double *tflops);
 
 /* ---- Z-slab decomposition across GPUs (one handle per GPU) ------------------
  * A slab handle keeps `cutoff` ghost planes below and above its own planes.

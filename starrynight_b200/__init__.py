@@ -31,7 +31,7 @@ EXPORTS = [
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_set_counters",
     "sn_get_sweep_count", "sn_set_sweep_count", "sn_set_replica_seed", "sn_site_energy",
     "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_recombination_partial", "sn_recombination_finish", "sn_get_boundary",
-    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak", "sn_philox_kat", "sn_state_hash", "sn_kernel_in_use",
+    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak", "sn_bench_fp64_peak", "sn_philox_kat", "sn_state_hash", "sn_kernel_in_use",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.sn_ipc_attach.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     lib.sn_attach_peer.argtypes = [H, C.c_int, H]
     lib.sn_bench_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.sn_bench_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sn_philox_kat.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sn_state_hash.argtypes = [H, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.sn_kernel_in_use.argtypes = [H, C.POINTER(C.c_int)]
@@ -305,14 +306,17 @@ class Simulation:
         _check(self.lib.sn_rdf(self.h, replica, fe.ctypes.data, afe.ctypes.data, cnt.ctypes.data))
         return fe, afe, cnt
 
-    def dipole_potential(self, replica=0):
-        v = np.zeros(self.nsites, np.float64)
+    def dipole_potential(self, replica=0, out=None):
+        """Potential map of the handle's sites (analysis.c:65-94); `out`: a C-contiguous float64 array of nsites (e.g. pinned)."""
+        v = np.zeros(self.nsites, np.float64) if out is None else out
+        assert v.dtype == np.float64 and v.size == self.nsites and v.flags.c_contiguous
         _check(self.lib.sn_potential_map(self.h, replica, v.ctypes.data))
         return v.reshape(self.X, self.Y, self.nz)
 
-    def dipole_electricfield(self, cutoff=4, half_offset=False, replica=0):
+    def dipole_electricfield(self, cutoff=4, half_offset=False, replica=0, out=None):
         """|E| per site: dipole_electricfield / dipole_electricfieldoffset (analysis.c:310-465)."""
-        v = np.zeros(self.nsites, np.float64)
+        v = np.zeros(self.nsites, np.float64) if out is None else out
+        assert v.dtype == np.float64 and v.size == self.nsites and v.flags.c_contiguous
         _check(self.lib.sn_efield_map(self.h, replica, int(cutoff), int(half_offset), v.ctypes.data))
         return v.reshape(self.X, self.Y, self.nz)
 
@@ -373,6 +377,11 @@ class Simulation:
         a = (C.c_ubyte * 64).from_buffer_copy(lattice_handle)
         b = (C.c_ubyte * 64).from_buffer_copy(flags_handle)
         _check(self.lib.sn_ipc_attach(self.h, side, a, b))
+
+    def fp64_peak_tflops(self):
+        out = C.c_double(0)
+        _check(self.lib.sn_bench_fp64_peak(self.params.device, C.byref(out)))
+        return out.value
 
     def fp32_peak_tflops(self):
         """FFMA microbenchmark on this handle's device (roofline denominator for bench.py)."""

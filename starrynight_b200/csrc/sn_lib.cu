@@ -860,10 +860,10 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
     const int CUT = sno::RDF_R;                     // analysis.c:540
     SnLatView view; int rc = sn_make_view(h, replica, CUT, "sn_rdf", &view);
     if (rc) return rc;
+    static_assert(SN_RDF_BINS == sno::RDF_NBINS, "bin count");
     std::vector<SnRdfOffset> off;
     std::vector<long long> mult(SN_RDF_BINS, 0);    // lattice vectors per r^2 (both signs): the reference's count per site
-    const int zc = h->G.gz > 0 ? CUT : CUT;         // the reference walks dz in [-9, 9] whatever Z is (% wraps it)
-    for (int dx = -CUT; dx <= CUT; dx++) for (int dy = -CUT; dy <= CUT; dy++) for (int dz = -zc; dz <= zc; dz++) {
+    for (int dx = -CUT; dx <= CUT; dx++) for (int dy = -CUT; dy <= CUT; dy++) for (int dz = -CUT; dz <= CUT; dz++) {   // dz in [-9, 9] whatever Z is (% wraps it)
         const int r2 = dx * dx + dy * dy + dz * dz;
         if (r2 >= SN_RDF_BINS) continue;            // r^2 == 81 is neither zeroed nor printed by the reference
         mult[r2]++;
@@ -871,9 +871,10 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
         if (!(dx > 0 || (dx == 0 && dy > 0) || (dx == 0 && dy == 0 && dz >= 0))) continue;
         SnRdfOffset o;
         o.delta = (dx * sno::RDF_NY + dy) * sno::RDF_NZ + dz; o.r2 = r2;
-        o.dx = dx; o.dy = dy; o.dz = dz; o.k = r2 > 0 ? 3.0 / (double)r2 : 0.0;
+        o.dx = dx; o.dy = dy; o.dz = dz;
         off.push_back(o);
     }
+    if ((int)off.size() > sno::RDF_NOFF) return sn_fail(SN_ERR_CUDA, "sn_rdf: internal: %d offsets in the half space, table holds %d", (int)off.size(), sno::RDF_NOFF);
     std::stable_sort(off.begin(), off.end(), [](const SnRdfOffset &a, const SnRdfOffset &b) { return a.r2 < b.r2; });
     std::vector<int> first(SN_RDF_BINS + 1, 0);
     for (auto &o : off) first[o.r2 + 1]++;
@@ -881,15 +882,13 @@ extern "C" int sn_rdf(sn_handle *h, int replica, double *fe_sum, double *afe_sum
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     const int nblocks = sn_obs_blocks(h), nv = 2 * SN_RDF_BINS;
     const size_t b_part = sizeof(double) * nv * (size_t)nblocks, b_tot = sizeof(double) * nv;
-    const size_t b_off = ((off.size() * sizeof(SnRdfOffset) + 15) / 16) * 16, b_first = first.size() * sizeof(int);
-    void *s; if ((rc = sn_scratch(h, b_part + b_tot + b_off + b_first + 256, &s))) return rc;
+    void *s; if ((rc = sn_scratch(h, b_part + b_tot + 256, &s))) return rc;
     double *d_part = (double *)s, *d_tot = d_part + (size_t)nv * nblocks;
-    SnRdfOffset *d_off = (SnRdfOffset *)((char *)s + b_part + b_tot);
-    int *d_first = (int *)((char *)d_off + b_off);
-    SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(SnRdfOffset), cudaMemcpyHostToDevice, h->stream));
-    SN_CUDA_CHECK(cudaMemcpyAsync(d_first, first.data(), b_first, cudaMemcpyHostToDevice, h->stream));
+    // the table is identical for every handle of the device; re-sending the same bytes under a running kernel is harmless
+    SN_CUDA_CHECK(cudaMemcpyToSymbolAsync(sn_c_rdf_off, off.data(), off.size() * sizeof(SnRdfOffset), 0, cudaMemcpyHostToDevice, h->stream));
+    SN_CUDA_CHECK(cudaMemcpyToSymbolAsync(sn_c_rdf_first, first.data(), first.size() * sizeof(int), 0, cudaMemcpyHostToDevice, h->stream));
     SN_CUDA_CHECK(cudaFuncSetAttribute(sn_rdf_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sno::RDF_SMEM));
-    sn_rdf_tiled_kernel<<<nblocks, sno::THREADS, sno::RDF_SMEM, h->stream>>>(view, h->G, d_off, d_first, SN_RDF_BINS, d_part);
+    sn_rdf_tiled_kernel<<<nblocks, sno::THREADS, sno::RDF_SMEM, h->stream>>>(view, h->G, d_part);
     sn_reduce_rows_kernel<<<nv, 256, 0, h->stream>>>(d_part, nblocks, nv, d_tot);
     SN_CUDA_CHECK(cudaGetLastError());
     std::vector<double> tot(nv);
@@ -910,14 +909,17 @@ static int sn_potential_device(sn_handle *h, int replica, size_t extra_bytes, do
     SnLatView view; int rc = sn_make_view(h, replica, MAXR, "sn_potential_map", &view);
     if (rc) return rc;
     std::vector<SnPotOffset> off;
+    int pitch, step; sn_obs_layout(sno::POT_N, &pitch, &step);
     for (int dx = -MAXR; dx <= MAXR; dx++) for (int dy = -MAXR; dy <= MAXR; dy++) for (int dz = -MAXR; dz <= MAXR; dz++) {
         if (!dx && !dy && !dz) continue;
         const double d = sqrt((double)(dx * dx + dy * dy + dz * dz));
         if (d > (double)MAXR) continue;
         const double w = 1.0 / (d * d * d);
-        SnPotOffset o; o.delta = (dx * sno::POT_N + dy) * sno::POT_N + dz; o.pad = 0; o.kx = dx * w; o.ky = dy * w; o.kz = dz * w;
+        SnPotOffset o; o.delta = (dx * sno::POT_N + dy) * pitch + dz; o.pad = 0; o.kx = dx * w; o.ky = dy * w; o.kz = dz * w;
         off.push_back(o);
     }
+    if ((int)off.size() > sno::POT_MAXOFF) return sn_fail(SN_ERR_CUDA, "sn_potential_map: internal: %d offsets", (int)off.size());
+    const int smem = sno::POT_N * sno::POT_N * pitch * 24 + (int)(off.size() * sizeof(SnPotOffset));
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
     const size_t b_v = ((sizeof(double) * n + 15) / 16) * 16, b_off = ((off.size() * sizeof(SnPotOffset) + 15) / 16) * 16;
     void *s; if ((rc = sn_scratch(h, b_v + b_off + extra_bytes + 64, &s))) return rc;
@@ -925,8 +927,8 @@ static int sn_potential_device(sn_handle *h, int replica, size_t extra_bytes, do
     SnPotOffset *d_off = (SnPotOffset *)((char *)s + b_v);
     if (extra) *extra = (char *)s + b_v + b_off;
     SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(SnPotOffset), cudaMemcpyHostToDevice, h->stream));
-    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_potential_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sno::POT_SMEM));
-    sn_potential_tiled_kernel<<<sn_obs_blocks(h), sno::THREADS, sno::POT_SMEM, h->stream>>>(view, h->G, d_off, (int)off.size(), *d_v);
+    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_potential_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    sn_potential_tiled_kernel<<<sn_obs_blocks(h), sno::THREADS, smem, h->stream>>>(view, h->G, d_off, (int)off.size(), pitch, step, *d_v);
     SN_CUDA_CHECK(cudaGetLastError());
     return SN_OK;
 }
@@ -955,6 +957,7 @@ extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_off
     const bool tiled = reach <= 6;                  // the box of an 8^3 tile with a halo of 6 fits in shared memory
     if (!tiled && !h->G.periodic_z) return sn_fail(SN_ERR_UNSUPPORTED, "sn_efield_map: cutoff %d on a Z-slab handle (radius above 6)", cutoff);
     const int N = sno::T + 2 * reach;
+    int pitch, step; sn_obs_layout(N, &pitch, &step);
     std::vector<SnEfOffset> off; std::vector<SnEfOffset2> off2;
     for (int dx = lo; dx <= hi; dx++) for (int dy = lo; dy <= hi; dy++) for (int dz = lo; dz <= hi; dz++) {
         if (!half_offset && !dx && !dy && !dz) continue;
@@ -964,7 +967,7 @@ extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_off
         SnEfOffset o; o.dx = (short)dx; o.dy = (short)dy; o.dz = (short)dz; o.pad = 0;
         o.nx = rx / d; o.ny = ry / d; o.nz = rz / d; o.w = 1.0 / (d * d * d);
         off.push_back(o);
-        SnEfOffset2 q; q.delta = (dx * N + dy) * N + dz; q.pad = 0; q.nx = o.nx; q.ny = o.ny; q.nz = o.nz; q.w = o.w;
+        SnEfOffset2 q; q.delta = (dx * N + dy) * pitch + dz; q.pad[0] = q.pad[1] = q.pad[2] = 0; q.nx = o.nx; q.ny = o.ny; q.nz = o.nz; q.w = o.w;
         off2.push_back(q);
     }
     const long long n = (long long)h->G.X * h->G.Y * h->G.nz;
@@ -976,10 +979,11 @@ extern "C" int sn_efield_map(sn_handle *h, int replica, int cutoff, int half_off
     if (tiled) {
         SnLatView view;
         if ((rc = sn_make_view(h, replica, reach, "sn_efield_map", &view))) return rc;
-        const int smem = N * N * N * 24;
+        const int smem = N * N * pitch * 24 + (int)(off2.size() * sizeof(SnEfOffset2));
+        if (smem > 227 * 1024) return sn_fail(SN_ERR_UNSUPPORTED, "sn_efield_map: cutoff %d needs %d bytes of shared memory", cutoff, smem);
         SN_CUDA_CHECK(cudaMemcpyAsync(d_off, off2.data(), off2.size() * sizeof(SnEfOffset2), cudaMemcpyHostToDevice, h->stream));
-        SN_CUDA_CHECK(cudaFuncSetAttribute(sn_efield_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sno::POT_SMEM));
-        sn_efield_tiled_kernel<<<sn_obs_blocks(h), sno::THREADS, smem, h->stream>>>(view, h->G, (const SnEfOffset2 *)d_off, (int)off2.size(), reach,
+        SN_CUDA_CHECK(cudaFuncSetAttribute(sn_efield_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        sn_efield_tiled_kernel<<<sn_obs_blocks(h), sno::THREADS, smem, h->stream>>>(view, h->G, (const SnEfOffset2 *)d_off, (int)off2.size(), reach, pitch, step,
                                                                                       half_offset ? 0 : 1, d_v);
     } else {
         if ((rc = sn_sync_canonical(h))) return rc;
@@ -1117,6 +1121,49 @@ extern "C" int sn_bench_fp32_peak(int device, double *tflops)
     for (int rep = 0; rep < 5; rep++) {
         SN_CUDA_CHECK(cudaEventRecord(e0));
         sn_ffma_peak_kernel<<<blocks, 256>>>(out, iters, 0.999f, 0.001f);
+        SN_CUDA_CHECK(cudaEventRecord(e1));
+        SN_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SN_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * 256;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return SN_OK;
+}
+
+// ---- FP64 roofline denominator (observables: every pair term is accumulated in FP64) -------------
+__global__ void __launch_bounds__(256) sn_dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int sn_bench_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return sn_fail(SN_ERR_INVALID, "sn_bench_fp64_peak: null");
+    SN_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SN_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1024;
+    double *out;
+    SN_CUDA_CHECK(cudaMalloc(&out, sizeof(double) * blocks * 256));
+    cudaEvent_t e0, e1;
+    SN_CUDA_CHECK(cudaEventCreate(&e0));
+    SN_CUDA_CHECK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        SN_CUDA_CHECK(cudaEventRecord(e0));
+        sn_dfma_peak_kernel<<<blocks, 256>>>(out, iters, 0.999, 0.001);
         SN_CUDA_CHECK(cudaEventRecord(e1));
         SN_CUDA_CHECK(cudaEventSynchronize(e1));
         float ms = 0.f;

@@ -194,7 +194,7 @@ __device__ __forceinline__ int wrap(int v, int n) { v %= n; return v < 0 ? v + n
 // put(cell, float4), cell = (lx * ny + ly) * nzb + lz.  One (x, y) row per warp at a time, the lanes along z (the
 // contiguous direction of the lattice): two integer divisions per row instead of per cell.
 template <class Put>
-__device__ __forceinline__ void sn_load_box(const SnLatView &view, const SnGeom &G, int bx0, int by0, int bz0, int nx, int ny, int nzb, Put &&put)
+__device__ __forceinline__ void sn_load_box(const SnLatView &view, const SnGeom &G, int bx0, int by0, int bz0, int nx, int ny, int nzb, int pitch, Put &&put)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int row = warp; row < nx * ny; row += nwarps) {
@@ -203,9 +203,29 @@ __device__ __forceinline__ void sn_load_box(const SnLatView &view, const SnGeom 
         for (int lz = lane; lz < nzb; lz += 32) {
             int z = bz0 + lz;
             if (G.periodic_z) z = sno::wrap(z, G.nz);
-            put(row * nzb + lz, sn_view_site(view, G, x, y, z));
+            put(row * pitch + lz, sn_view_site(view, G, x, y, z));
         }
     }
+}
+
+// Site of the 8^3 tile owned by thread slot t (0..511) in the kernels that keep the box as FP64 component arrays.
+// Eight lanes run along z (64 B of one row); the two rows of a half-warp must fall into complementary halves of the 32
+// banks, i.e. lie `step` rows apart with (step * pitch * 8) % 128 == 64 (sn_obs_layout picks pitch and step): the
+// 8-byte loads of a warp then cost the minimum of two wavefronts instead of four.
+__device__ __forceinline__ void sn_obs_site(int t, int step, int &lx, int &ly, int &lz)
+{
+    lz = t & 7; lx = t >> 6;
+    const int a = (t >> 3) & 1, r = (t >> 4) & 3;
+    ly = step == 1 ? a + 2 * r : step == 2 ? 2 * a + (r & 1) + 4 * (r >> 1) : 4 * a + r;
+}
+
+// z pitch (in cells) and row step for a box of n cells per axis
+inline void sn_obs_layout(int n, int *pitch, int *step)
+{
+    for (int p = n; p <= n + 2; p++)
+        for (int s = 1; s <= 4; s *= 2)
+            if ((s * p * 8) % 128 == 64) { *pitch = p; *step = s; return; }
+    *pitch = n; *step = 1;                        // not reached for even n
 }
 
 __device__ __forceinline__ void sn_tile_origin(const SnGeom &G, int &x0, int &y0, int &z0)
@@ -232,18 +252,23 @@ __global__ void __launch_bounds__(256) sn_reduce_rows_kernel(const double *__res
 // r^2 > 0 (half the 3071 pair terms per site).  The half space walked is dx > 0, or dx = 0 and dy > 0, or
 // dx = dy = 0 and dz >= 0, so the box is 17 x 26 x 26 sites (184 KB as float4).  FP64 throughout, block-reduced
 // once per bin -> out[block][bin][2]; sn_reduce_rows_kernel adds the blocks.
-struct SnRdfOffset { int delta; int r2; double dx, dy, dz, k; };     // delta: box index step; k = 3 / r^2 (0 at the origin)
+struct SnRdfOffset { double dx, dy, dz; int delta; int r2; };       // delta: box index step (32 B per entry)
 namespace sno { constexpr int RDF_R = 9, RDF_NX = T + RDF_R, RDF_NY = T + 2 * RDF_R, RDF_NZ = T + 2 * RDF_R;
-                constexpr int RDF_SMEM = RDF_NX * RDF_NY * RDF_NZ * 16; }
+                constexpr int RDF_SMEM = RDF_NX * RDF_NY * RDF_NZ * 16, RDF_NOFF = 1488, RDF_NBINS = 81; }   // 1485 lattice vectors with r^2 <= 80 in the half space
+// The offset table is the same for every lattice (radius 9, fixed box): constant memory, read with a warp-uniform
+// index -- no global-memory latency in the pair loop (the first tiled version spent 37 % of its stall samples there).
+__constant__ SnRdfOffset sn_c_rdf_off[sno::RDF_NOFF];
+__constant__ int sn_c_rdf_first[sno::RDF_NBINS + 1];
 
-__global__ void __launch_bounds__(sno::THREADS, 1) sn_rdf_tiled_kernel(const SnLatView view, const SnGeom G, const SnRdfOffset *__restrict__ off,
-                                                                       const int *__restrict__ first, int nbins, double *__restrict__ out)
+// Per pair term and site: FE += a.c (3 DFMA straight into the accumulator), S += (d.a)(d.c) (7 DFMA); the AFE sum of a
+// bin is FE - (3 / r^2) S with the factor applied once per bin (n = d / |d|, analysis.c:571-576; the origin has n = 0).
+__global__ void __launch_bounds__(sno::THREADS, 1) sn_rdf_tiled_kernel(const SnLatView view, const SnGeom G, double *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char sn_obs_smem[];
     float4 *box = reinterpret_cast<float4 *>(sn_obs_smem);
     __shared__ double sm[2 * 8];
     int x0, y0, z0; sn_tile_origin(G, x0, y0, z0);
-    sn_load_box(view, G, x0, y0 - sno::RDF_R, z0 - sno::RDF_R, sno::RDF_NX, sno::RDF_NY, sno::RDF_NZ, [&](int i, float4 v) { box[i] = v; });
+    sn_load_box(view, G, x0, y0 - sno::RDF_R, z0 - sno::RDF_R, sno::RDF_NX, sno::RDF_NY, sno::RDF_NZ, sno::RDF_NZ, [&](int i, float4 v) { box[i] = v; });
     __syncthreads();
     int base[2]; bool live[2]; double ax[2], ay[2], az[2];
 #pragma unroll
@@ -254,25 +279,28 @@ __global__ void __launch_bounds__(sno::THREADS, 1) sn_rdf_tiled_kernel(const SnL
         const float4 a = box[base[s]];
         ax[s] = live[s] ? (double)a.x : 0.0; ay[s] = live[s] ? (double)a.y : 0.0; az[s] = live[s] ? (double)a.z : 0.0;   // a dead site adds exact zeros
     }
-    for (int b = 0; b < nbins; b++) {
-        const int o0 = first[b], o1 = first[b + 1];
-        double v[2] = {0.0, 0.0};
-#pragma unroll 2
+    for (int b = 0; b < sno::RDF_NBINS; b++) {
+        const int o0 = sn_c_rdf_first[b], o1 = sn_c_rdf_first[b + 1];
+        double fe[2] = {0.0, 0.0}, sq[2] = {0.0, 0.0};
+#pragma unroll 4
         for (int o = o0; o < o1; o++) {
-            const SnRdfOffset f = off[o];
+            const double dx = sn_c_rdf_off[o].dx, dy = sn_c_rdf_off[o].dy, dz = sn_c_rdf_off[o].dz;
+            const int delta = sn_c_rdf_off[o].delta;
 #pragma unroll
             for (int s = 0; s < 2; s++) {
-                const float4 c = box[base[s] + f.delta];
+                const float4 c = box[base[s] + delta];
                 const double cx = c.x, cy = c.y, cz = c.z;
-                const double fe = ax[s] * cx + ay[s] * cy + az[s] * cz;
-                const double na = f.dx * ax[s] + f.dy * ay[s] + f.dz * az[s];
-                const double nc = f.dx * cx + f.dy * cy + f.dz * cz;
-                v[0] += fe;
-                v[1] += fe - f.k * na * nc;                 // fe - 3 (n.a)(n.c), n = d / |d| (analysis.c:574-576); k = 0 at the origin (:571-573)
+                fe[s] = fma(ax[s], cx, fma(ay[s], cy, fma(az[s], cz, fe[s])));
+                const double na = fma(dx, ax[s], fma(dy, ay[s], dz * az[s]));
+                const double nc = fma(dx, cx, fma(dy, cy, dz * cz));
+                sq[s] = fma(na, nc, sq[s]);
             }
         }
+        double v[2];
+        v[0] = fe[0] + fe[1];
+        v[1] = v[0] - (b > 0 ? 3.0 / (double)b : 0.0) * (sq[0] + sq[1]);
         if (o1 > o0) sn_block_sum<2, sno::THREADS>(v, sm);      // uniform across the block
-        if (threadIdx.x == 0) { out[((long long)blockIdx.x * nbins + b) * 2] = v[0]; out[((long long)blockIdx.x * nbins + b) * 2 + 1] = v[1]; }
+        if (threadIdx.x == 0) { out[((long long)blockIdx.x * sno::RDF_NBINS + b) * 2] = v[0]; out[((long long)blockIdx.x * sno::RDF_NBINS + b) * 2 + 1] = v[1]; }
     }
 }
 
@@ -280,61 +308,66 @@ __global__ void __launch_bounds__(sno::THREADS, 1) sn_rdf_tiled_kernel(const SnL
 // V_i = sum_{0 < d <= 6} l_j (p_j . r) / d^3.  The box holds the moments m_j = l_j p_j as doubles (the product of two
 // floats is exact in double), component-wise arrays so that consecutive lanes read consecutive words; the offset
 // table holds r / d^3.  3 FMA and 3 shared-memory loads per pair term.
-struct SnPotOffset { int delta; int pad; double kx, ky, kz; };
-namespace sno { constexpr int POT_R = 6, POT_N = T + 2 * POT_R, POT_CELLS = POT_N * POT_N * POT_N, POT_SMEM = POT_CELLS * 24; }
+struct SnPotOffset { double kx, ky, kz; int delta; int pad; };      // 32 B: two broadcast LDS.128 per term
+namespace sno { constexpr int POT_R = 6, POT_N = T + 2 * POT_R, POT_MAXOFF = 1024; }
 
 __global__ void __launch_bounds__(sno::THREADS, 1) sn_potential_tiled_kernel(const SnLatView view, const SnGeom G, const SnPotOffset *__restrict__ off,
-                                                                             int noff, double *__restrict__ V)
+                                                                             int noff, int pitch, int step, double *__restrict__ V)
 {
     extern __shared__ __align__(16) unsigned char sn_obs_smem[];
-    double *mx = reinterpret_cast<double *>(sn_obs_smem), *my = mx + sno::POT_CELLS, *mz = my + sno::POT_CELLS;
+    const int cells = sno::POT_N * sno::POT_N * pitch;
+    double *mx = reinterpret_cast<double *>(sn_obs_smem), *my = mx + cells, *mz = my + cells;
+    SnPotOffset *tab = reinterpret_cast<SnPotOffset *>(mz + cells);
     int x0, y0, z0; sn_tile_origin(G, x0, y0, z0);
-    sn_load_box(view, G, x0 - sno::POT_R, y0 - sno::POT_R, z0 - sno::POT_R, sno::POT_N, sno::POT_N, sno::POT_N,
+    for (int i = threadIdx.x; i < noff; i += sno::THREADS) tab[i] = off[i];
+    sn_load_box(view, G, x0 - sno::POT_R, y0 - sno::POT_R, z0 - sno::POT_R, sno::POT_N, sno::POT_N, sno::POT_N, pitch,
                 [&](int i, float4 v) { mx[i] = (double)v.w * v.x; my[i] = (double)v.w * v.y; mz[i] = (double)v.w * v.z; });
     __syncthreads();
     int base[2]; double pot[2] = {0.0, 0.0};
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
-        base[s] = ((lx + sno::POT_R) * sno::POT_N + ly + sno::POT_R) * sno::POT_N + lz + sno::POT_R;
+        int lx, ly, lz; sn_obs_site(threadIdx.x + s * sno::THREADS, step, lx, ly, lz);
+        base[s] = ((lx + sno::POT_R) * sno::POT_N + ly + sno::POT_R) * pitch + lz + sno::POT_R;
     }
 #pragma unroll 4
     for (int o = 0; o < noff; o++) {
-        const SnPotOffset f = off[o];
+        const SnPotOffset f = tab[o];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             const int c = base[s] + f.delta;
-            pot[s] += mx[c] * f.kx + my[c] * f.ky + mz[c] * f.kz;
+            pot[s] = fma(mx[c], f.kx, fma(my[c], f.ky, fma(mz[c], f.kz, pot[s])));
         }
     }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
+        int lx, ly, lz; sn_obs_site(threadIdx.x + s * sno::THREADS, step, lx, ly, lz);
         if (x0 + lx < G.X && y0 + ly < G.Y && z0 + lz < G.nz) V[((long long)(x0 + lx) * G.Y + y0 + ly) * G.nz + z0 + lz] = pot[s];
     }
 }
 
 // ---- dipole electric-field maps, tiled (analysis.c:310-376, 393-465); reach <= 6 --------------------
-struct SnEfOffset2 { int delta; int pad; double nx, ny, nz, w; };    // n = r / d, w = 1 / d^3
+struct __align__(16) SnEfOffset2 { double nx, ny, nz, w; int delta; int pad[3]; };    // n = r / d, w = 1 / d^3; 48 B
 
 __global__ void __launch_bounds__(sno::THREADS, 1) sn_efield_tiled_kernel(const SnLatView view, const SnGeom G, const SnEfOffset2 *__restrict__ off,
-                                                                          int noff, int reach, int self_term, double *__restrict__ Emag)
+                                                                          int noff, int reach, int pitch, int step, int self_term, double *__restrict__ Emag)
 {
     extern __shared__ __align__(16) unsigned char sn_obs_smem[];
-    const int N = sno::T + 2 * reach, cells = N * N * N;
+    const int N = sno::T + 2 * reach, cells = N * N * pitch;
     double *px = reinterpret_cast<double *>(sn_obs_smem), *py = px + cells, *pz = py + cells;
+    SnEfOffset2 *tab = reinterpret_cast<SnEfOffset2 *>(pz + cells);
     int x0, y0, z0; sn_tile_origin(G, x0, y0, z0);
-    sn_load_box(view, G, x0 - reach, y0 - reach, z0 - reach, N, N, N, [&](int i, float4 v) { px[i] = v.x; py[i] = v.y; pz[i] = v.z; });
+    for (int i = threadIdx.x; i < noff; i += sno::THREADS) tab[i] = off[i];
+    sn_load_box(view, G, x0 - reach, y0 - reach, z0 - reach, N, N, N, pitch, [&](int i, float4 v) { px[i] = v.x; py[i] = v.y; pz[i] = v.z; });
     __syncthreads();
     int base[2]; double ex[2] = {0.0, 0.0}, ey[2] = {0.0, 0.0}, ez[2] = {0.0, 0.0};
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
-        base[s] = ((lx + reach) * N + ly + reach) * N + lz + reach;
+        int lx, ly, lz; sn_obs_site(threadIdx.x + s * sno::THREADS, step, lx, ly, lz);
+        base[s] = ((lx + reach) * N + ly + reach) * pitch + lz + reach;
     }
 #pragma unroll 2
     for (int o = 0; o < noff; o++) {
-        const SnEfOffset2 f = off[o];
+        const SnEfOffset2 f = tab[o];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             const int c = base[s] + f.delta;
@@ -347,7 +380,7 @@ __global__ void __launch_bounds__(sno::THREADS, 1) sn_efield_tiled_kernel(const 
     }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        const int t = threadIdx.x + s * sno::THREADS, lz = t & 7, ly = (t >> 3) & 7, lx = t >> 6;
+        int lx, ly, lz; sn_obs_site(threadIdx.x + s * sno::THREADS, step, lx, ly, lz);
         if (!(x0 + lx < G.X && y0 + ly < G.Y && z0 + lz < G.nz)) continue;
         if (self_term) { ex[s] -= px[base[s]] / 3.0; ey[s] -= py[base[s]] / 3.0; ez[s] -= pz[base[s]] / 3.0; }   // analysis.c:457-459
         Emag[((long long)(x0 + lx) * G.Y + y0 + ly) * G.nz + z0 + lz] = sqrt(ex[s] * ex[s] + ey[s] * ey[s] + ez[s] * ez[s]);
