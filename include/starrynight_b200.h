@@ -114,7 +114,10 @@ SN_API int sn_get_lattice(sn_handle *h, int replica, float *xyzlen);
 SN_API int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzlen);
 SN_API int sn_get_lattice_async(sn_handle *h, int replica, float *xyzlen);
 /* h's later work waits (on the device) for the sweeps queued so far on `other`: fixes the order of the two handles'
- * persistent sweep kernels when they are used as a double buffer. */
+ * persistent sweep kernels when they are used as a double buffer.  Z-slab handles that share a GPU normally split its
+ * SMs (their kernels may have to be resident together); handles ordered this way never run at once and are given
+ * the whole share from the first call on -- the caller must then keep ordering every launch, in the same order on
+ * every GPU of the decomposition. */
 SN_API int sn_order_after(sn_handle *h, sn_handle *other);
 
 /* replaces assignments to the globals beta (main.c:215,239), Efield (config.c:132-134),

@@ -199,6 +199,7 @@ struct sn_handle {
     unsigned long long spin_timeout_ns = 60ull * 1000000000ull;   // bound of device-side waits (env SN_SPIN_TIMEOUT_S)
     int num_sms = 148;
     int grid_limit = 0;                 // > 0: cap on the tiled kernel's persistent grid (slab neighbours sharing this device)
+    const void *serial_group = nullptr; // handles whose sweeps the caller serialises (sn_order_after) share one group: they never run at once
     void *tmap = nullptr;               // CUtensorMap storage for the tiled kernel (device-constant copy made at launch)
     float *audit_dev = nullptr;         // set for the duration of sn_mc_sweep_audit: the sweep kernels record every attempt
     // scratch

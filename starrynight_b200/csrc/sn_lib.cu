@@ -118,17 +118,26 @@ static int sn_build_neighbours(sn_handle *h)
 static std::mutex sn_slab_registry_mutex;
 static std::vector<sn_handle *> sn_slab_registry;
 
+// (registry mutex held) SM share of every registered handle: the SMs of a device are divided among the groups of
+// handles that can be resident at once.  Handles the caller serialises with sn_order_after form one group.
+static void sn_slab_shares()
+{
+    for (sn_handle *a : sn_slab_registry) {
+        std::vector<const void *> groups;
+        for (sn_handle *b : sn_slab_registry)
+            if (b->p.device == a->p.device && std::find(groups.begin(), groups.end(), b->serial_group) == groups.end()) groups.push_back(b->serial_group);
+        const int n = (int)groups.size();
+        a->grid_limit = n > 1 ? std::max(1, a->num_sms / n) : 0;
+    }
+}
+
 static void sn_slab_register(sn_handle *h, bool add)
 {
     std::lock_guard<std::mutex> lock(sn_slab_registry_mutex);
     auto it = std::find(sn_slab_registry.begin(), sn_slab_registry.end(), h);
     if (add && it == sn_slab_registry.end()) sn_slab_registry.push_back(h);
     if (!add && it != sn_slab_registry.end()) sn_slab_registry.erase(it);
-    for (sn_handle *a : sn_slab_registry) {
-        int n = 0;
-        for (sn_handle *b : sn_slab_registry) n += b->p.device == a->p.device;
-        a->grid_limit = n > 1 ? std::max(1, a->num_sms / n) : 0;
-    }
+    sn_slab_shares();
 }
 
 // (E_x, E_y, E_z, CageStrain) of one replica -> device (the sweep kernels read the four together)
@@ -253,6 +262,7 @@ extern "C" int sn_create(const sn_params *p, sn_handle **out)
     sn_handle *h = new sn_handle();
     h->p = *p;
     if (h->p.nz <= 0) { h->p.nz = p->Z; h->p.z0 = 0; }
+    h->serial_group = h;
     h->G.periodic_z = 1;                              // until the geometry is known: sn_destroy must not touch the slab registry
     if (h->p.z0 < 0 || h->p.z0 + h->p.nz > p->Z) {
         const int z0 = h->p.z0, nz = h->p.nz;
@@ -562,6 +572,15 @@ extern "C" int sn_order_after(sn_handle *h, sn_handle *other)
     SN_CHECK_HANDLE(h, 0);
     if (!other) return sn_fail(SN_ERR_INVALID, "sn_order_after: null");
     SN_CUDA_CHECK(cudaStreamWaitEvent(h->stream, other->ev_sweeps, 0));
+    if (h->serial_group != other->serial_group) {
+        // from now on the two are one job as far as SM sharing goes: their persistent kernels never run at once,
+        // so each may use every SM its group is entitled to (the caller keeps ordering them, on every GPU alike)
+        std::lock_guard<std::mutex> lock(sn_slab_registry_mutex);
+        const void *from = h->serial_group;
+        for (sn_handle *a : sn_slab_registry) if (a->serial_group == from) a->serial_group = other->serial_group;
+        h->serial_group = other->serial_group;
+        sn_slab_shares();
+    }
     return SN_OK;
 }
 
