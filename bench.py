@@ -91,6 +91,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--size", type=int, default=None, help="lattice edge override for the cubic workloads")
+    ap.add_argument("--shape", default=None, help="X,Y,Z override (experiments: e.g. the per-GPU slab shape of a larger run)")
     ap.add_argument("--sweeps-per-step", type=int, default=None)
     ap.add_argument("--replicas", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU sample for cpu_baseline")
@@ -100,6 +101,8 @@ def parse_args():
     w = dict(WORKLOADS[a.workload])
     if a.size:
         w["shape"] = (a.size, a.size, a.size if w["shape"][2] > 1 else 1)
+    if a.shape:
+        w["shape"] = tuple(int(v) for v in a.shape.split(","))
     if a.sweeps_per_step:
         w["sweeps"] = a.sweeps_per_step
     if a.replicas:
