@@ -281,8 +281,9 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.004):
         self.index = index
+        self.period = period
         self.rows = []          # (sm_mhz, reasons bitmask or set)
         self.max_mhz = None
         self.proc = None
@@ -332,7 +333,7 @@ class ClockSampler:
                 self.rows.append((mhz, {k for k, b in bits.items() if mask & b}))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(self.period)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -699,7 +700,7 @@ def run_analysis(args):
         one_pass()
     parts.clear()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period=0.05)         # many short synchronous calls here: NVML queries every 4 ms would slow rank 0 down
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
