@@ -354,7 +354,11 @@ __device__ __forceinline__ void sn_store_pair2(float4 *__restrict__ lat2, float4
     if (ix && iy) put(lat2, x + ix, y + iy, z);
     if (iz) {
         // periodic z: images in this array; Z-slab: the same planes live in the neighbour's ghost shell
+#ifdef SN_EXP_NOREMOTE
+        float4 *__restrict__ dst = G.periodic_z ? lat2 : nullptr;
+#else
         float4 *__restrict__ dst = G.periodic_z ? lat2 : (iz > 0 ? peer_lo : peer_hi);
+#endif
         if (dst) {
             put(dst, x, y, z + iz);
             if (ix) put(dst, x + ix, y, z + iz);
@@ -458,32 +462,44 @@ __device__ __forceinline__ bool sn_tile_deps_ready(const SnTileFlow &f, const Sn
         const unsigned int need = (unsigned int)it.sweep + (q < it.p ? 1u : 0u);
         const unsigned int *src = f.ver + sn_ver_index(f, it.rep, ntx, nty, ntz + 1);
         unsigned int v;
-        if (f.sys_scope && (ntz < 0 || ntz >= f.tnz)) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+#ifdef SN_EXP_GPUACQ
+        const bool remote_entry = false;
+#else
+        const bool remote_entry = f.sys_scope && (ntz < 0 || ntz >= f.tnz);
+#endif
+        if (remote_entry) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
         else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
         ok = (int)(v - need) >= 0;
     }
     return __all_sync(0xffffffffu, ok);
 }
 
-// One thread, after every store of the tile (write-back, ghost images, pushes to the neighbours) has been fenced.
+// One thread, after every store of the tile (write-back, ghost images, pushes to the neighbours) has been fenced at CTA
+// scope by the workers and observed through the arrival counter.  ONE fence at the scope the readers need, then relaxed
+// stores of the version words (fence + relaxed store is a release pattern; a st.release per word would cost a MEMBAR
+// each -- with pushes to a neighbour GPU in flight every system-scope MEMBAR waits for an NVLink round trip, which
+// made 64-plane slabs 13 % slower than the same tiles on one GPU).
 __device__ __forceinline__ void sn_tile_publish(const SnTileFlow &f, const SnTileItem &it)
 {
     const unsigned int v = (unsigned int)it.sweep + 1u;
     unsigned int *own = f.ver + sn_ver_index(f, it.rep, it.tx, it.ty, it.tz + 1);
     unsigned int *glo = it.tz == 0 ? f.peer_ver_lo + sn_ver_index(f, it.rep, it.tx, it.ty, f.tnz + 1) : nullptr;
     unsigned int *ghi = it.tz == f.tnz - 1 ? f.peer_ver_hi + sn_ver_index(f, it.rep, it.tx, it.ty, 0) : nullptr;
+#ifdef SN_EXP_GPUFENCE
+    if (false) {
+#else
     if (f.sys_scope && (glo || ghi)) {
-        // a boundary tile: its pushes into the neighbour GPU's ghost planes (fenced at GPU scope by the
-        // threads that made them, observed here through the arrival counter) become visible system-wide
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(own), "r"(v) : "memory");
-        if (glo) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(glo), "r"(v) : "memory");
-        if (ghi) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ghi), "r"(v) : "memory");
+#endif
+        // a boundary tile: its pushes into the neighbour GPU's ghost planes become visible system-wide before the versions
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(own), "r"(v) : "memory");
+        if (glo) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(glo), "r"(v) : "memory");
+        if (ghi) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(ghi), "r"(v) : "memory");
     } else {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(own), "r"(v) : "memory");
-        if (glo) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(glo), "r"(v) : "memory");
-        if (ghi) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ghi), "r"(v) : "memory");
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(own), "r"(v) : "memory");
+        if (glo) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(glo), "r"(v) : "memory");
+        if (ghi) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ghi), "r"(v) : "memory");
     }
 }
 
@@ -609,6 +625,14 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
             cta_sync();                                   // hand-over: every worker has read its part of the tile
             if (ready && lane == 0) issue_tile_load(nxt);
             while ((int)(*reinterpret_cast<volatile unsigned int *>(ctl_arrive) - done) < 0) __nanosleep(40);
+            __syncwarp();
+            // one more look at the next item before the (possibly slow) publication: if its dependencies have arrived in
+            // the meantime, its load goes first (it cannot depend on `cur` then, whose version is still the old one)
+            if (nxt.valid && !ready && sn_tile_deps_ready(fl, nxt, lane)) {
+                ready = true;
+                deps_met();
+                if (lane == 0) issue_tile_load(nxt);
+            }
             __syncwarp();
             if (lane == 0) sn_tile_publish(fl, cur);
             if (nxt.valid && !ready) {
