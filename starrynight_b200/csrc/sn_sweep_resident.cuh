@@ -164,8 +164,17 @@ bool sn_resident_supported(const sn_handle *h, std::string *why)
     return true;
 }
 
+// Sweeps per launch: the kernel counts accepted / rejected / vacant attempts in 32-bit registers per thread and adds them
+// up over a warp before they go to the 64-bit counters, so one launch may make at most 2^31 attempts per warp.
+static long long sn_resident_chunk(const sn_handle *h, int threads)
+{
+    const long long sites = (long long)h->G.X * h->G.Y * h->G.Z;
+    const long long per_warp = 32 * ((sites + threads - 1) / threads);       // attempts of one warp per sweep, at most
+    return std::max<long long>(1, std::min<long long>(1LL << 30, ((1LL << 31) - 1) / per_warp));
+}
+
 template <int MODE, bool SPECIES>
-static int sn_resident_launch_t(sn_handle *h, const SnSweepArgs &a, long long nsweeps)
+static int sn_resident_launch_t(sn_handle *h, const SnSweepArgs &a, long long nsweeps, long long *launches)
 {
     const snr::Layout L = snr::layout(h->G, h->p.cutoff, a.ax.P, a.ay.P, a.az.P);
     const int smem = snr::smem_bytes(h->G, L);
@@ -173,10 +182,12 @@ static int sn_resident_launch_t(sn_handle *h, const SnSweepArgs &a, long long ns
     SN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = std::min(h->p.nreplicas, h->num_sms);
     long long done = 0;
-    while (done < nsweeps) {                              // the kernel's sweep count is an int
-        const int chunk = (int)std::min<long long>(nsweeps - done, 1 << 30);
+    const long long limit = sn_resident_chunk(h, snr::threads(MODE));
+    while (done < nsweeps) {
+        const int chunk = (int)std::min<long long>(nsweeps - done, limit);
         kern<<<grid, snr::threads(MODE), smem, h->stream>>>(a, L, h->p.nreplicas, h->sweep + (unsigned long long)done, chunk);
         done += chunk;
+        if (launches) (*launches)++;
     }
     SN_CUDA_CHECK(cudaGetLastError());
     return SN_OK;
@@ -190,12 +201,11 @@ int sn_sweep_resident_launch(sn_handle *h, long long nsweeps, long long *launche
     const SnSweepArgs a = sn_sweep_args(h);
     const int mode = h->p.cutoff == 3 ? (h->p.Z == 1 ? 1 : 0) : 2;
     int rc;
-    if (mode == 0) rc = h->species ? sn_resident_launch_t<0, true>(h, a, nsweeps) : sn_resident_launch_t<0, false>(h, a, nsweeps);
-    else if (mode == 1) rc = h->species ? sn_resident_launch_t<1, true>(h, a, nsweeps) : sn_resident_launch_t<1, false>(h, a, nsweeps);
-    else rc = sn_resident_launch_t<2, true>(h, a, nsweeps);
+    if (mode == 0) rc = h->species ? sn_resident_launch_t<0, true>(h, a, nsweeps, launches) : sn_resident_launch_t<0, false>(h, a, nsweeps, launches);
+    else if (mode == 1) rc = h->species ? sn_resident_launch_t<1, true>(h, a, nsweeps, launches) : sn_resident_launch_t<1, false>(h, a, nsweeps, launches);
+    else rc = sn_resident_launch_t<2, true>(h, a, nsweeps, launches);
     if (rc) return rc;
     h->sweep += (unsigned long long)nsweeps;
-    if (launches) *launches += (nsweeps + (1LL << 30) - 1) >> 30;
     if ((rc = sn_refresh_ghosts(h))) return rc;           // the kernel wrote interior cells only
     if (launches) (*launches)++;
     return SN_OK;
