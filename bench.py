@@ -700,7 +700,7 @@ def run_analysis(args):
         one_pass()
     parts.clear()
     barrier()
-    sampler = ClockSampler(local, period=0.05)         # many short synchronous calls here: NVML queries every 4 ms would slow rank 0 down
+    sampler = ClockSampler(local, period=0.25)         # many short synchronous calls here: frequent NVML queries contend with the launches and slow rank 0 down
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
