@@ -79,8 +79,8 @@ constexpr int SITE_THREADS = 128;        // threads of one role; each owns 2 sit
 constexpr int OFF_XF = OFF_END;                 // partial fields handed from role B to role A: float2[2 buffers][3][128]
 constexpr int OFF_XP = OFF_XF + 2 * 3 * SITE_THREADS * 8;      // proposals drawn by role B: float4[2 buffers][2 sites][128]
 constexpr int OFF_BAR = OFF_XP + 2 * 2 * SITE_THREADS * 16;    // mbarrier
-constexpr int OFF_CTL = OFF_BAR + 16;                          // control warp hand-over: SnTileItem (48 B) + two arrival counters
-constexpr int SMEM_BYTES = OFF_CTL + 64;
+constexpr int OFF_CTL = OFF_BAR + 16;                          // control warp hand-over: two SnTileItem slots (48 B each) + two arrival counters
+constexpr int SMEM_BYTES = OFF_CTL + 112;
 constexpr int WORKERS = 256;                // 2 roles x 4 warps
 constexpr int THREADS = WORKERS + 32;      // + the control warp
 // Column pairs (snt::col numbering) gathered by role A.  Role B works one super-pass ahead of role A's
@@ -514,9 +514,12 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
     float2 *tile_z = reinterpret_cast<float2 *>(smem + snt::OFF_Z);         // ... (z0, z1)
     float2 *tile_l = reinterpret_cast<float2 *>(smem + snt::OFF_L);         // ... (l0, l1), SPECIES only
     const uint32_t bar = sn_smem_u32(smem + snt::OFF_BAR);
+    // The hand-over slot alternates: the control warp may prepare the next item (slot n + 1) as soon as its dependencies are
+    // met, while a slow worker warp is still reading the current one (slot n) behind the previous hand-over barrier.
     SnTileItem *ctl_item = reinterpret_cast<SnTileItem *>(smem + snt::OFF_CTL);
-    unsigned int *ctl_wbread = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 48);   // worker warps that reached the write-back
-    unsigned int *ctl_arrive = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 52);   // worker warps whose stores are fenced
+    unsigned int *ctl_wbread = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 96);   // worker warps that reached the write-back
+    unsigned int *ctl_arrive = reinterpret_cast<unsigned int *>(smem + snt::OFF_CTL + 100);  // worker warps whose stores are fenced
+    int slot = 0;
 
     // Two roles of 128 threads (4 warps) each -- one warp of each role per scheduler, so that one
     // role's issue slots fill the other's latency gaps:
@@ -602,7 +605,7 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
             deps_met();
             if (lane == 0) issue_tile_load(cur);
         }
-        if (lane == 0) *ctl_item = cur;
+        if (lane == 0) ctl_item[0] = cur;
         __syncwarp();
         cta_sync();
         for (unsigned int done = 8; cur.valid; done += 8) {
@@ -620,7 +623,8 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
             ready = ready && nxt.valid;
             if (ready) deps_met();
             nxt.ready = ready;
-            if (lane == 0) *ctl_item = nxt;
+            slot ^= 1;
+            if (lane == 0) ctl_item[slot] = nxt;
             __syncwarp();
             cta_sync();                                   // hand-over: every worker has read its part of the tile
             if (ready && lane == 0) issue_tile_load(nxt);
@@ -648,7 +652,7 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
     // ---- workers -----------------------------------------------------------------------------------
     auto workers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(snt::WORKERS) : "memory"); };
     cta_sync();
-    SnTileItem item = *ctl_item;
+    SnTileItem item = ctl_item[0];
 
     while (item.valid) {
         const int x0 = item.x0, y0 = item.y0, z0 = item.z0, rep = item.rep;
@@ -846,7 +850,8 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
             if (lane == 0) atomicAdd(ctl_wbread, 1u);     // tells the control warp to stop polling and come to the hand-over
             __syncwarp();
             cta_sync();                                   // hand-over: the control warp starts the next TMA load
-            nxt = *ctl_item;
+            slot ^= 1;
+            nxt = ctl_item[slot];
             float4 *gxy = glat;                                                            // pairs of the xy array
             float2 *gz2 = reinterpret_cast<float2 *>(reinterpret_cast<float *>(glat) + 2 * rs2);   // pairs of the z array
             const long long gbase = sn_pidx2(G, x0, y0, z0 + 2 * pr) >> 1;
