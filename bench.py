@@ -19,8 +19,8 @@ analysis_midpoint) in sites/s; the default line is unchanged.
          step's lattice from pinned host memory (sn_set_lattice_async), fills the slab
          ghost planes device to device (sn_pull_ghosts), sweeps, and reads the lattice
          and counters back (sn_get_lattice_async, sn_get_counters).  Successive steps
-         are independent batches, so two handles are used alternately: step i+1's
-         upload and step i-1's download travel over PCIe while step i is swept
+         are independent batches, so two handles are used in
+         rotation: step i+1's upload and step i-1's download travel over PCIe while step i is swept
          (copies at PCIe rate cannot be hidden inside one 20-sweep step: 2 x 2.1 GB at
          ~55 GB/s is 78 ms beside 115-145 ms of sweeps).  ``e2e.serial`` is the same
          loop with one handle and synchronous calls.
@@ -485,28 +485,32 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers -------------------------------------
     e2e = None
     if not args.no_e2e:
-        outs = [[torch.empty_like(host_of(r)).pin_memory() for r in range(reps)] for _ in range(2)]
+        # handles used in rotation.  Three were measured too (profiles/r02_bench_c5_n8_three_handles.json): no gain -- where the
+        # copies outlast the sweeps (8 GPUs) the host side is saturated and the loop runs at the serial sum either way
+        NH = 2
+        outs = [[torch.empty_like(host_of(r)).pin_memory() for r in range(reps)] for _ in range(NH)]
         h2d = sum(host_of(r).numel() * 4 for r in range(reps))
         d2h = h2d + 24 * reps
-        sims = [sim, make_sim()]
-        wire(sims[1])
+        sims = [sim] + [make_sim() for _ in range(NH - 1)]
+        for s_ in sims[1:]:
+            wire(s_)
 
         def e2e_loop(nsteps, pipelined):
             barrier()
             t0 = time.perf_counter()
             for i in range(nsteps):
-                s, o = (sims[i % 2], sims[(i + 1) % 2]) if pipelined else (sims[0], None)
+                s, o = (sims[i % NH], sims[(i - 1) % NH]) if pipelined else (sims[0], None)
                 s.synchronize()                       # its previous download has landed: host buffers are free again
-                if i >= (2 if pipelined else 1):
+                if i >= (NH if pipelined else 1):
                     s.counters()                      # the step's result: ACCEPT / REJECT (and the lattice in outs)
                 for r in range(reps):
                     s.set_lattice_async(host_of(r).data_ptr(), r)     # H2D from pinned memory
                 if o is not None:
-                    s.order_after(o)                  # the two handles' sweep kernels keep one order on every GPU
+                    s.order_after(o)                  # the handles' sweep kernels keep one order on every GPU
                 s.pull_ghosts()                       # slab ghost planes, device to device, handshake included
                 step(s, False)
                 for r in range(reps):
-                    s.get_lattice_async(outs[i % 2][r].data_ptr(), r)  # D2H
+                    s.get_lattice_async(outs[i % NH][r].data_ptr(), r)  # D2H
             for s in (sims if pipelined else sims[:1]):
                 s.synchronize()
                 s.counters()
@@ -518,16 +522,17 @@ def run_ours(args):
                 dt = float(t.item())
             return dt
 
-        e2e_loop(2, True)                             # warm-up (staging buffers, pinned mappings)
+        e2e_loop(NH, True)                            # warm-up (staging buffers, pinned mappings)
         dt_pipe = e2e_loop(args.steps, True)
         e2e_loop(1, False)
         dt_serial = e2e_loop(args.steps, False)
         e2e = {"value": attempts_step * args.steps / dt_pipe, "unit": UNIT, "h2d_bytes_per_step": h2d * n, "d2h_bytes_per_step": d2h * n,
-               "mode": "two handles used alternately: step i+1's upload and step i-1's download overlap step i's sweeps; every step's "
-                       "lattice is uploaded from and downloaded to pinned host memory inside the timed region",
+               "mode": "%d handles used in rotation: step i+1's upload and step i-1's download overlap step i's sweeps; every step's "
+                       "lattice is uploaded from and downloaded to pinned host memory inside the timed region" % NH,
                "serial": {"value": attempts_step * args.steps / dt_serial, "mode": "one handle, each step upload -> sweeps -> download back to back"},
                "seconds": dt_pipe}
-        sims[1].close()
+        for s_ in sims[1:]:
+            s_.close()
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks = {}
