@@ -181,6 +181,8 @@ struct sn_handle {
     std::vector<char> rep_species;      // per replica: some length != 1
     unsigned int *rep_species_dev = nullptr;   // device: raised by the upload kernel, read lazily (sn_resolve_species)
     bool species_dirty = false;
+    unsigned int *rep_species_host = nullptr;  // pinned mirror of the flags, filled behind every upload ...
+    cudaEvent_t ev_species = nullptr;          // ... and complete when this event is: sn_resolve_species waits for the UPLOAD only, not for the stream
     bool use_tiled = false;
     bool use_resident = false;          // lattice small enough to live in one CTA's shared memory (sn_sweep_resident.cuh)
     // The tiled kernel works on a second copy of the lattice in the split layout (sn_pidx2 / sn_ld2 / sn_st2).

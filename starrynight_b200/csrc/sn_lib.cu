@@ -184,6 +184,8 @@ static int sn_create_body(sn_handle *h, const sn_params *p)
     SN_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_sweeps, cudaEventDisableTiming));
     SN_CUDA_CHECK(cudaMalloc(&h->rep_species_dev, sizeof(unsigned int) * p->nreplicas));
     SN_CUDA_CHECK(cudaMemsetAsync(h->rep_species_dev, 0, sizeof(unsigned int) * p->nreplicas, h->stream));
+    SN_CUDA_CHECK(cudaMallocHost(&h->rep_species_host, sizeof(unsigned int) * p->nreplicas));
+    SN_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_species, cudaEventDisableTiming));
     const size_t cells = (size_t)G.rep_stride * p->nreplicas;
     if (cudaMalloc(&h->lat, cells * sizeof(float4)) != cudaSuccess) {
         cudaGetLastError();
@@ -291,6 +293,8 @@ extern "C" int sn_destroy(sn_handle *h)
     for (int e = 0; e < 2; e++) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
     if (h->ev_sweeps) cudaEventDestroy(h->ev_sweeps);
     cudaFree(h->rep_species_dev);
+    if (h->rep_species_host) cudaFreeHost(h->rep_species_host);
+    if (h->ev_species) cudaEventDestroy(h->ev_species);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SN_OK;
@@ -375,16 +379,16 @@ static int sn_staging(sn_handle *h, float4 **out)
     return SN_OK;
 }
 
-// The species flags are raised on the device by the upload; the host looks at them only when it next has to
-// choose a kernel specialisation (sweep launch), so an upload never blocks.
+// The species flags are raised on the device by the upload and copied to a pinned mirror right behind it; the host looks
+// at them only when it next has to choose a kernel specialisation (sweep launch), and then waits for that copy alone --
+// not for whatever else has been queued on the stream since (a wait for another handle's sweeps, the slab handshake):
+// a stream-wide synchronisation here made the double-buffered end-to-end loop on two GPUs 25 % slower.
 int sn_resolve_species(sn_handle *h)
 {
     if (!h->species_dirty) return SN_OK;
-    std::vector<unsigned int> f(h->p.nreplicas);
-    SN_CUDA_CHECK(cudaMemcpyAsync(f.data(), h->rep_species_dev, sizeof(unsigned int) * h->p.nreplicas, cudaMemcpyDeviceToHost, h->stream));
-    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    SN_CUDA_CHECK(cudaEventSynchronize(h->ev_species));
     h->species = false;
-    for (int r = 0; r < h->p.nreplicas; r++) { h->rep_species[r] = f[r] != 0; h->species = h->species || f[r] != 0; }
+    for (int r = 0; r < h->p.nreplicas; r++) { h->rep_species[r] = h->rep_species_host[r] != 0; h->species = h->species || h->rep_species_host[r] != 0; }
     h->species_dirty = false;
     return SN_OK;
 }
@@ -412,6 +416,8 @@ extern "C" int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzl
         h->lat_valid = true; h->lat2_valid = false;
     }
     SN_CUDA_CHECK(cudaGetLastError());
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->rep_species_host, h->rep_species_dev, sizeof(unsigned int) * h->p.nreplicas, cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaEventRecord(h->ev_species, h->stream));
     h->species_dirty = true;
     return SN_OK;
 }
