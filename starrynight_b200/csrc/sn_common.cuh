@@ -181,6 +181,9 @@ struct sn_handle {
     std::vector<char> rep_species;      // per replica: some length != 1
     unsigned int *rep_species_dev = nullptr;   // device: raised by the upload kernel, read lazily (sn_resolve_species)
     bool species_dirty = false;
+    // couplings (beta, field, cage strain) travel through a ring of pinned slots: the copies are stream-ordered and the
+    // calls return at once (a field ramp with one sweep per point must not synchronise the stream at every point)
+    float4 *coupling_ring = nullptr; unsigned long long ring_pos = 0;
     unsigned int *rep_species_host = nullptr;  // pinned mirror of the flags, filled behind every upload ...
     cudaEvent_t ev_species = nullptr;          // ... and complete when this event is: sn_resolve_species waits for the UPLOAD only, not for the stream
     bool use_tiled = false;

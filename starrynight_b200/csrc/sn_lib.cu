@@ -141,11 +141,20 @@ static void sn_slab_register(sn_handle *h, bool add)
 }
 
 // (E_x, E_y, E_z, CageStrain) of one replica -> device (the sweep kernels read the four together)
+constexpr unsigned long long SN_RING_SLOTS = 4096;
+// next pinned slot of the coupling ring; when the ring wraps, the copies that used the old contents must have run
+static int sn_ring_slot(sn_handle *h, float4 **slot)
+{
+    if (h->ring_pos && h->ring_pos % SN_RING_SLOTS == 0) SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    *slot = h->coupling_ring + h->ring_pos++ % SN_RING_SLOTS;
+    return SN_OK;
+}
+
 static int sn_push_couplings(sn_handle *h, int r)
 {
-    const float4 e4 = make_float4(h->h_efield[3 * r], h->h_efield[3 * r + 1], h->h_efield[3 * r + 2], (float)h->h_cage[r]);
-    SN_CUDA_CHECK(cudaMemcpyAsync(h->efield + r, &e4, sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));      // e4 lives on this stack frame
+    float4 *slot; int rc = sn_ring_slot(h, &slot); if (rc) return rc;
+    *slot = make_float4(h->h_efield[3 * r], h->h_efield[3 * r + 1], h->h_efield[3 * r + 2], (float)h->h_cage[r]);
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->efield + r, slot, sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     return SN_OK;
 }
 
@@ -185,6 +194,7 @@ static int sn_create_body(sn_handle *h, const sn_params *p)
     SN_CUDA_CHECK(cudaMalloc(&h->rep_species_dev, sizeof(unsigned int) * p->nreplicas));
     SN_CUDA_CHECK(cudaMemsetAsync(h->rep_species_dev, 0, sizeof(unsigned int) * p->nreplicas, h->stream));
     SN_CUDA_CHECK(cudaMallocHost(&h->rep_species_host, sizeof(unsigned int) * p->nreplicas));
+    SN_CUDA_CHECK(cudaMallocHost(&h->coupling_ring, sizeof(float4) * SN_RING_SLOTS));
     SN_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_species, cudaEventDisableTiming));
     const size_t cells = (size_t)G.rep_stride * p->nreplicas;
     if (cudaMalloc(&h->lat, cells * sizeof(float4)) != cudaSuccess) {
@@ -294,6 +304,7 @@ extern "C" int sn_destroy(sn_handle *h)
     if (h->ev_sweeps) cudaEventDestroy(h->ev_sweeps);
     cudaFree(h->rep_species_dev);
     if (h->rep_species_host) cudaFreeHost(h->rep_species_host);
+    if (h->coupling_ring) cudaFreeHost(h->coupling_ring);
     if (h->ev_species) cudaEventDestroy(h->ev_species);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -461,8 +472,9 @@ extern "C" int sn_set_beta(sn_handle *h, int replica, double beta)
 {
     SN_CHECK_HANDLE(h, replica);
     h->h_beta[replica] = (float)beta;
-    SN_CUDA_CHECK(cudaMemcpyAsync(h->beta + replica, &h->h_beta[replica], sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    SN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    float4 *slot; int rc = sn_ring_slot(h, &slot); if (rc) return rc;
+    slot->x = (float)beta;
+    SN_CUDA_CHECK(cudaMemcpyAsync(h->beta + replica, &slot->x, sizeof(float), cudaMemcpyHostToDevice, h->stream));
     return SN_OK;
 }
 
