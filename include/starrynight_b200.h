@@ -121,7 +121,8 @@ SN_API int sn_get_lattice_async(sn_handle *h, int replica, float *xyzlen);
 SN_API int sn_order_after(sn_handle *h, sn_handle *other);
 
 /* replaces assignments to the globals beta (main.c:215,239), Efield (config.c:132-134),
- * CageStrain (main.c:149) between MC_moves calls */
+ * CageStrain (main.c:149) between MC_moves calls.  Stream-ordered: the new value applies to the sweeps queued after the
+ * call (and to the audit / energy entry points called after it); the calls do not wait for earlier sweeps to finish. */
 SN_API int sn_set_beta(sn_handle *h, int replica, double beta);
 SN_API int sn_set_efield(sn_handle *h, int replica, const float E[3]);
 SN_API int sn_set_cagestrain(sn_handle *h, double cagestrain);           /* every replica */
