@@ -217,8 +217,7 @@ static int sn_create_body(sn_handle *h, const sn_params *p)
         // phase flags, the tiled kernel's work counter and its tile-version array (one allocation, so that a
         // slab neighbour reaches all of it through one IPC handle)
         size_t nflags = SN_FLAGS_VER;
-        if (G.X % 16 == 0 && G.Y % 16 == 0 && G.nz % 16 == 0)
-            h->nver = (size_t)p->nreplicas * (G.X / 16) * (G.Y / 16) * (G.nz / 16 + 2);
+        h->nver = (size_t)p->nreplicas * ((G.X + 15) / 16) * ((G.Y + 15) / 16) * ((G.nz + 15) / 16 + 2);       // partial tiles count
         nflags += h->nver;
         SN_CUDA_CHECK(cudaMalloc(&h->flags, sizeof(unsigned int) * nflags));
         SN_CUDA_CHECK(cudaMemsetAsync(h->flags, 0, sizeof(unsigned int) * nflags, h->stream));

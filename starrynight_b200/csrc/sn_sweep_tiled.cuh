@@ -1,7 +1,8 @@
 // sn_sweep_tiled.cuh -- the fast Metropolis sweep: TMA-staged shared-memory tiles.
 //
 // Replaces MC_moves -> MC_move -> site_energy (montecarlo-core.c:76-191) for
-// DipoleCutOff = 3 lattices whose X, Y and slab height are multiples of 32.
+// DipoleCutOff = 3 lattices with X, Y, Z >= 32 and Z a multiple of 4 (Z-slab handles: multiples of 32 planes); the last
+// tile of an axis may be partial, an odd number of tiles along an axis gets a third tile colour.
 //
 // Decomposition
 //   * The lattice is cut into 16^3 tiles.  A sweep is 8 "phases", one per tile
@@ -668,7 +669,9 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
         float4 *glat = a.lat + (long long)rep * rs2;
         float4 *plo = a.peer_lo ? a.peer_lo + (long long)rep * rs2 : nullptr;
         float4 *phi = a.peer_hi ? a.peer_hi + (long long)rep * rs2 : nullptr;
-        const bool face_tile = x0 == 0 || x0 + snt::T == G.X || y0 == 0 || y0 + snt::T == G.Y || z0 == 0 || z0 + snt::T == G.nz;
+        // (a partial tile -- extents need not be multiples of 16 -- ends at the lattice face: its cells beyond the face are
+        // zero-filled by the TMA unit, never attempted and never written back)
+        const bool face_tile = x0 == 0 || x0 + snt::T >= G.X || y0 == 0 || y0 + snt::T >= G.Y || z0 == 0 || z0 + snt::T >= G.nz;
 
         // Trial orientations for the thread's 2 sites in super-pass sp from ONE Philox4x32-10 call keyed by
         // (global site of the first one, replica, sweep): per site 64 random bits = 32 (accept) + 20 + 20, the low 8
@@ -718,6 +721,7 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
             if (role == 0) {
                 const int cx = sp >> 2, cy = sp & 3;
                 const int gx = x0 + cx + 4 * i, gy = y0 + cy + 4 * j, gz = z0 + 4 * k + 2 * h;
+                const bool live = gx < G.X && gy < G.Y && gz < G.nz;         // false only in the cells of a partial tile beyond the lattice
                 const int cell = ((snt::H + cx + 4 * i) * snt::BX + (snt::H + cy + 4 * j)) * snt::NP + pair0;
                 const SnTileCol tc{tile_xy + cell, tile_z + cell, tile_l + cell};
                 float3 F[2], Gc[2];
@@ -777,7 +781,7 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
                         if (d1 == 1) dE += cg[s].x * dpS[t2].x + cg[s].y * dpS[t2].y + cg[s].z * dpS[t2].z;
                         if (d2 == 1) dE += cg[s].x * dpU[t2].x + cg[s].y * dpU[t2].y + cg[s].z * dpU[t2].z;
                     }
-                    const bool mine = h == (t4 >> 1);
+                    const bool mine = (h == (t4 >> 1)) & live;
 #ifdef SN_EXP_NOEXP
                     const bool acc = mine & !vac[s] & (dE < 0.0f);
 #else
@@ -859,7 +863,7 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
 #pragma unroll
             for (int pss = 0; pss < 8; pss++) {
                 const int row = pss * 32 + row0, lx = row >> 4, ly = row & 15;
-                if (face_tile) sn_store_pair2(glat, plo, phi, G, rs2, x0 + lx, y0 + ly, z0 + 2 * pr, wbx[pss], wbz[pss]);
+                if (face_tile) { if (x0 + lx < G.X && y0 + ly < G.Y && z0 + 2 * pr < G.nz) sn_store_pair2(glat, plo, phi, G, rs2, x0 + lx, y0 + ly, z0 + 2 * pr, wbx[pss], wbz[pss]); }
                 else { gxy[gbase + lx * sx2 + ly * sy2] = wbx[pss]; gz2[gbase + lx * sx2 + ly * sy2] = wbz[pss]; }
             }
         }
@@ -899,7 +903,8 @@ bool sn_tiled_supported(const sn_handle *h, std::string *why)
     const char *msg = nullptr;
     if (h->p.cutoff != 3) msg = "DipoleCutOff must be 3";
     else if (G.Z == 1) msg = "lattice is flat (Z == 1)";
-    else if (G.X % 16 || G.Y % 16 || G.nz % 16 || G.X < 32 || G.Y < 32 || G.nz < 32) msg = "X, Y and Z must be multiples of 16, at least 32";
+    else if (G.X < 32 || G.Y < 32 || G.nz < 32) msg = "X, Y and Z must be at least 32";
+    else if (G.nz % 4) msg = "Z must be a multiple of 4 (a thread's two sites and a segment of 4 must not straddle the lattice's end)";
     else if (!G.periodic_z && (G.nz % 32 || G.z0 % 32 || G.Z % 32)) msg = "Z-slabs: Z, slab height and slab origin must be multiples of 32";
     if (msg) { if (why) *why = msg; return false; }
     return true;
@@ -987,7 +992,7 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
     SnSweepArgs a = sn_sweep_args(h);
     a.lat = h->lat2;                                  // the kernel works on the split copies (own and neighbours')
     SnTileFlow f;
-    f.tnx = G.X / snt::T; f.tny = G.Y / snt::T; f.tnz = G.nz / snt::T; f.nrep = h->p.nreplicas;
+    f.tnx = (G.X + snt::T - 1) / snt::T; f.tny = (G.Y + snt::T - 1) / snt::T; f.tnz = (G.nz + snt::T - 1) / snt::T; f.nrep = h->p.nreplicas;   // the last tile of an axis may be partial
     f.ncx = sn_tc_ncol(f.tnx); f.ncy = sn_tc_ncol(f.tny); f.ncz = sn_tc_ncol(f.tnz); f.np = f.ncx * f.ncy * f.ncz;
     f.periodic_z = G.periodic_z;
     f.pre[0] = 0;
