@@ -55,7 +55,7 @@ def _run_split(sn, lat, nslab, kernel, sweeps, devices, per_call=1, pull=True):
     return out, counters, energy
 
 
-@pytest.mark.parametrize("shape,kernel", [((64, 32, 64), "tiled"), ((16, 12, 16), "colour"), ((32, 32, 128), "tiled")])
+@pytest.mark.parametrize("shape,kernel", [((64, 32, 64), "tiled"), ((16, 12, 16), "colour"), ((32, 32, 128), "tiled"), ((40, 52, 64), "tiled")])
 def test_two_slabs_match_one_gpu_bit_for_bit(sn, devices, shape, kernel):
     X, Y, Z = shape
     kid = sn.SN_KERNEL_TILED if kernel == "tiled" else sn.SN_KERNEL_COLOUR
