@@ -239,13 +239,14 @@ static int sn_create_body(sn_handle *h, const sn_params *p)
     const bool can_tile = sn_tiled_supported(h, &why);
     if ((p->kernel == SN_KERNEL_TILED || p->kernel == SN_KERNEL_TILED_PHASED) && !can_tile)
         return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: tiled kernel unavailable: %s", why.c_str());
-    h->use_tiled = can_tile && p->kernel != SN_KERNEL_COLOUR && p->kernel != SN_KERNEL_RESIDENT;
     {
         std::string why_r;
         const bool can_reside = sn_resident_supported(h, &why_r);
         if (p->kernel == SN_KERNEL_RESIDENT && !can_reside)
             return sn_fail(SN_ERR_UNSUPPORTED, "sn_create: shared-memory-resident kernel unavailable: %s", why_r.c_str());
-        h->use_resident = can_reside && !h->use_tiled && (p->kernel == SN_KERNEL_AUTO || p->kernel == SN_KERNEL_RESIDENT);
+        // a lattice that fits one CTA's shared memory stays there (replica batches fill the GPU); the tiles take the rest
+        h->use_resident = can_reside && (p->kernel == SN_KERNEL_AUTO || p->kernel == SN_KERNEL_RESIDENT);
+        h->use_tiled = can_tile && !h->use_resident && p->kernel != SN_KERNEL_COLOUR && p->kernel != SN_KERNEL_RESIDENT;
     }
     if (h->use_tiled) { int rc = sn_tiled_prepare(h); if (rc) return rc; }
     {

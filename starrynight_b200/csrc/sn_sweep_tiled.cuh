@@ -1,7 +1,7 @@
 // sn_sweep_tiled.cuh -- the fast Metropolis sweep: TMA-staged shared-memory tiles.
 //
 // Replaces MC_moves -> MC_move -> site_energy (montecarlo-core.c:76-191) for
-// DipoleCutOff = 3 lattices with X, Y, Z >= 32 and Z a multiple of 4 (Z-slab handles: multiples of 32 planes); the last
+// DipoleCutOff = 3 lattices with X, Y, Z >= 20 and Z a multiple of 4 (Z-slab handles: multiples of 32 planes); the last
 // tile of an axis may be partial, an odd number of tiles along an axis gets a third tile colour.
 //
 // Decomposition
@@ -903,7 +903,9 @@ bool sn_tiled_supported(const sn_handle *h, std::string *why)
     const char *msg = nullptr;
     if (h->p.cutoff != 3) msg = "DipoleCutOff must be 3";
     else if (G.Z == 1) msg = "lattice is flat (Z == 1)";
-    else if (G.X < 32 || G.Y < 32 || G.nz < 32) msg = "X, Y and Z must be at least 32";
+    // two tiles per axis at least, and a tile's box must not hold images of the tile's own sites: the lower halo of the
+    // first tile shows the sites X-3 .. X-1, which must lie beyond its 16 own columns (X >= 19)
+    else if (G.X < 20 || G.Y < 20 || G.nz < 20) msg = "X, Y and Z must be at least 20";
     else if (G.nz % 4) msg = "Z must be a multiple of 4 (a thread's two sites and a segment of 4 must not straddle the lattice's end)";
     else if (!G.periodic_z && (G.nz % 32 || G.z0 % 32 || G.Z % 32)) msg = "Z-slabs: Z, slab height and slab origin must be multiples of 32";
     if (msg) { if (why) *why = msg; return false; }

@@ -191,7 +191,7 @@ def test_equilibrium_observables_match_reference_chain(sn, T, Ex):
 @pytest.mark.parametrize("shape,reps,calls", [((32, 32, 32), 1, (3,)), ((64, 64, 64), 1, (2, 3)), ((96, 64, 32), 2, (4,)),
                                               ((160, 96, 64), 1, (3, 1)), ((256, 256, 64), 1, (2,)),
                                               ((48, 48, 48), 2, (2, 1)), ((80, 48, 32), 1, (3,)), ((112, 32, 144), 1, (2,)),
-                                              ((100, 44, 36), 1, (2, 1)), ((33, 50, 40), 2, (3,))])
+                                              ((100, 44, 36), 1, (2, 1)), ((33, 50, 40), 2, (3,)), ((20, 21, 28), 1, (3,)), ((64, 30, 20), 2, (2,))])
 def test_dataflow_launch_equals_barrier_separated_phases(sn, shape, reps, calls):
     """The tiled kernel runs whole sweeps in one launch, ordering adjacent tiles through per-tile version
     counters instead of a barrier per tile-parity phase.  The chain must be bit-identical to the same
@@ -276,10 +276,10 @@ def test_resident_kernel_equals_colour_passes_bit_for_bit(sn, case):
 
 
 @pytest.mark.parametrize("shape,want", [((48, 48, 48), "tiled"), ((80, 96, 112), "tiled"), ((100, 100, 100), "tiled"), ((45, 37, 36), "tiled"),
-                                        ((100, 100, 98), "colour"), ((32, 32, 16), "colour"),
+                                        ((100, 100, 98), "colour"), ((32, 32, 16), "colour"), ((64, 64, 28), "tiled"), ((30, 30, 32), "tiled"),
                                         ((64, 64, 64), "tiled"), ((20, 20, 28), "resident"), ((100, 100, 1), "resident")])
 def test_kernel_selection(sn, shape, want):
-    """SN_KERNEL_AUTO: the tiled kernel takes every cut-off-3 lattice with X, Y, Z >= 32 and Z a multiple of 4 -- the last tile
+    """SN_KERNEL_AUTO: the tiled kernel takes every cut-off-3 lattice with X, Y, Z >= 20 and Z a multiple of 4 that does not fit the resident kernel -- the last tile
     of an axis may be partial, an odd number of tiles along an axis gets a third tile colour -- small lattices live in shared
     memory, the rest runs colour passes."""
     ids = {"tiled": sn.SN_KERNEL_TILED, "colour": sn.SN_KERNEL_COLOUR, "resident": sn.SN_KERNEL_RESIDENT}
