@@ -199,6 +199,12 @@ SN_API int sn_polarisation(sn_handle *h, int replica, double P[3]);
 SN_API int sn_state_hash(sn_handle *h, int replica, unsigned long long *hash);
 /* which sweep kernel sn_mc_sweeps runs on this handle (an sn_kernel value other than SN_KERNEL_AUTO) */
 SN_API int sn_kernel_in_use(sn_handle *h, int *kernel);
+
+/* Diagnostic (host only, no GPU needed): the work order of the tiled kernel for one sweep of a periodic X x Y x Z lattice --
+ * items[n][5] = {replica, tile x, tile y, tile z, phase} in the order the persistent CTAs take them; *n_items = tiles x
+ * replicas.  Adjacent tiles (26-neighbourhood, periodic) never share a phase; an item starts once its neighbours have
+ * finished the items that precede it in this order.  items may be NULL to query the count. */
+SN_API int sn_tile_schedule(int X, int Y, int Z, int nreplicas, unsigned long long sweep, int *n_items, int *items, int max_items);
 /* replaces landau_order() (analysis.c:506-526): |sum_i p_i|^2 / N * N as written there */
 SN_API int sn_landau_order(sn_handle *h, int replica, double *landau);
 /* Observables on a Z-slab handle cover the handle's own sites; planes beyond the slab are read from the neighbouring

@@ -31,7 +31,7 @@ EXPORTS = [
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_set_counters",
     "sn_get_sweep_count", "sn_set_sweep_count", "sn_set_replica_seed", "sn_site_energy",
     "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_recombination_partial", "sn_recombination_finish", "sn_get_boundary",
-    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak", "sn_bench_fp64_peak", "sn_philox_kat", "sn_state_hash", "sn_kernel_in_use",
+    "sn_set_ghost", "sn_ipc_export", "sn_ipc_attach", "sn_attach_peer", "sn_bench_fp32_peak", "sn_bench_fp64_peak", "sn_philox_kat", "sn_state_hash", "sn_kernel_in_use", "sn_tile_schedule",
 ]
 
 
@@ -128,6 +128,17 @@ def philox_kat(counter_key, device=False):
     dev = np.zeros((len(ck), 4), np.uint32) if device else None
     _check(load_library().sn_philox_kat(len(ck), ck.ctypes.data, host.ctypes.data, dev.ctypes.data if device else None))
     return host, dev
+
+
+def tile_schedule(X, Y, Z, nreplicas=1, sweep=0):
+    """Work order of the tiled kernel for one sweep (host logic only): int array [n][5] = replica, tx, ty, tz, phase."""
+    lib = load_library()
+    n = C.c_int(0)
+    lib.sn_tile_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(C.c_int), C.c_void_p, C.c_int]
+    _check(lib.sn_tile_schedule(X, Y, Z, nreplicas, sweep, C.byref(n), None, 0))
+    items = np.zeros((n.value, 5), np.int32)
+    _check(lib.sn_tile_schedule(X, Y, Z, nreplicas, sweep, C.byref(n), items.ctypes.data, n.value))
+    return items
 
 
 def recombination_finish(parts):

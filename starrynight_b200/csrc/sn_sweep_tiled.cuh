@@ -415,7 +415,7 @@ struct __align__(16) SnTileItem {
     int valid, ready;                   // (scheduler hand-over) item exists; its dependencies were met when polled
 };
 
-__device__ __forceinline__ SnTileItem sn_tile_item(const SnTileFlow &f, unsigned long long n)
+__host__ __device__ __forceinline__ SnTileItem sn_tile_item(const SnTileFlow &f, unsigned long long n)
 {
     SnTileItem it;
     it.valid = 1; it.ready = 0;
@@ -977,6 +977,40 @@ int sn_sync_canonical(sn_handle *h)
 static SnSweepArgs sn_sweep_args(sn_handle *h);
 static int sn_slab_phase_sync(sn_handle *h, long long *launches);
 
+// tile grid, colours and the items-per-phase prefix sums of a lattice (the last tile of an axis may be partial)
+static void sn_tile_flow_shape(SnTileFlow &f, int X, int Y, int nz, int nrep, int periodic_z)
+{
+    f.tnx = (X + snt::T - 1) / snt::T; f.tny = (Y + snt::T - 1) / snt::T; f.tnz = (nz + snt::T - 1) / snt::T; f.nrep = nrep;
+    f.ncx = sn_tc_ncol(f.tnx); f.ncy = sn_tc_ncol(f.tny); f.ncz = sn_tc_ncol(f.tnz); f.np = f.ncx * f.ncy * f.ncz;
+    f.periodic_z = periodic_z;
+    f.pre[0] = 0;
+    for (int p = 0; p < f.np; p++) {
+        const int cz = p % f.ncz, cy = (p / f.ncz) % f.ncy, cx = p / (f.ncz * f.ncy);
+        f.pre[p + 1] = f.pre[p] + (unsigned int)(sn_tc_count(f.tnx, cx) * sn_tc_count(f.tny, cy) * sn_tc_count(f.tnz, cz) * f.nrep);
+    }
+    for (int p = f.np + 1; p < 28; p++) f.pre[p] = f.pre[f.np];
+}
+
+// Host-side view of the tiled kernel's work order (no GPU involved): the items of sweep `sweep` of a periodic X x Y x Z
+// lattice in the order the persistent CTAs take them, items[n] = {replica, tx, ty, tz, phase}.  Diagnostic / test aid.
+extern "C" int sn_tile_schedule(int X, int Y, int Z, int nreplicas, unsigned long long sweep, int *n_items, int *items, int max_items)
+{
+    if (!n_items || X < 20 || Y < 20 || Z < 20 || Z % 4 || nreplicas < 1) return sn_fail(SN_ERR_INVALID, "sn_tile_schedule: bad arguments");
+    SnTileFlow f;
+    sn_tile_flow_shape(f, X, Y, Z, nreplicas, 1);
+    f.base_sweep = 0;
+    const unsigned long long S = f.pre[f.np];
+    *n_items = (int)S;
+    if (!items) return SN_OK;
+    if ((unsigned long long)max_items < S) return sn_fail(SN_ERR_INVALID, "sn_tile_schedule: %llu items, room for %d", S, max_items);
+    for (unsigned long long n = 0; n < S; n++) {
+        const SnTileItem it = sn_tile_item(f, sweep * S + n);
+        int *o = items + 5 * n;
+        o[0] = it.rep; o[1] = it.tx; o[2] = it.ty; o[3] = it.tz; o[4] = it.p;
+    }
+    return SN_OK;
+}
+
 int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
 {
     const SnGeom &G = h->G;
@@ -994,15 +1028,7 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
     SnSweepArgs a = sn_sweep_args(h);
     a.lat = h->lat2;                                  // the kernel works on the split copies (own and neighbours')
     SnTileFlow f;
-    f.tnx = (G.X + snt::T - 1) / snt::T; f.tny = (G.Y + snt::T - 1) / snt::T; f.tnz = (G.nz + snt::T - 1) / snt::T; f.nrep = h->p.nreplicas;   // the last tile of an axis may be partial
-    f.ncx = sn_tc_ncol(f.tnx); f.ncy = sn_tc_ncol(f.tny); f.ncz = sn_tc_ncol(f.tnz); f.np = f.ncx * f.ncy * f.ncz;
-    f.periodic_z = G.periodic_z;
-    f.pre[0] = 0;
-    for (int p = 0; p < f.np; p++) {
-        const int cz = p % f.ncz, cy = (p / f.ncz) % f.ncy, cx = p / (f.ncz * f.ncy);
-        f.pre[p + 1] = f.pre[p] + (unsigned int)(sn_tc_count(f.tnx, cx) * sn_tc_count(f.tny, cy) * sn_tc_count(f.tnz, cz) * f.nrep);
-    }
-    for (int p = f.np + 1; p < 28; p++) f.pre[p] = f.pre[f.np];
+    sn_tile_flow_shape(f, G.X, G.Y, G.nz, h->p.nreplicas, G.periodic_z);
     f.base_sweep = h->sweep;
     f.next = reinterpret_cast<unsigned long long *>(h->flags + SN_FLAGS_NEXT);
     f.ver = h->flags + SN_FLAGS_VER;
