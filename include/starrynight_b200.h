@@ -61,7 +61,7 @@ typedef enum {
     SN_KERNEL_AUTO = 0,    /* tiled kernel when the lattice allows it, the resident kernel when the lattice fits in one
                               CTA's shared memory, else colour passes */
     SN_KERNEL_COLOUR = 1,  /* one launch per colour sublattice, neighbours read from global memory */
-    SN_KERNEL_TILED = 2,   /* TMA-staged shared-memory tiles (needs cutoff 3, X, Y, nz >= 20, nz a multiple of 4; Z-slabs: multiples of 32 planes) */
+    SN_KERNEL_TILED = 2,   /* TMA-staged shared-memory tiles (needs cutoff 2 or 3, X, Y, nz >= 20, nz a multiple of 4; Z-slabs: multiples of 32 planes) */
     SN_KERNEL_RESIDENT = 4, /* lattice resident in shared memory, one CTA per replica, all sweeps of a call in one launch
                               (needs X*Y*Z*16 B <= 227 KB, no Z-slabs); bit-identical to SN_KERNEL_COLOUR */
     SN_KERNEL_TILED_PHASED = 3  /* the same kernel, one launch per tile-parity phase instead of one dataflow

@@ -1231,8 +1231,8 @@ static int sn_preload_kernels(int device)
         (const void *)sn_scatter_kernel<true>, (const void *)sn_scatter_kernel<false>,
         (const void *)sn_gather_kernel<true>, (const void *)sn_gather_kernel<false>,
         (const void *)sn_convert_layout_kernel, (const void *)sn_refresh_ghosts_kernel, (const void *)sn_fill_u32_kernel,
-        (const void *)sn_tiled_kernel<true, false>, (const void *)sn_tiled_kernel<false, false>,
-        (const void *)sn_tiled_kernel<true, true>, (const void *)sn_tiled_kernel<false, true>,
+        (const void *)sn_tiled_kernel<true, false, 3>, (const void *)sn_tiled_kernel<false, false, 3>, (const void *)sn_tiled_kernel<true, false, 2>, (const void *)sn_tiled_kernel<false, false, 2>,
+        (const void *)sn_tiled_kernel<true, true, 3>, (const void *)sn_tiled_kernel<false, true, 3>, (const void *)sn_tiled_kernel<true, true, 2>, (const void *)sn_tiled_kernel<false, true, 2>,
         (const void *)sn_colour_pass_kernel<0, true>, (const void *)sn_colour_pass_kernel<0, false>,
         (const void *)sn_colour_pass_kernel<1, true>, (const void *)sn_colour_pass_kernel<1, false>,
         (const void *)sn_colour_pass_kernel<2, true>,

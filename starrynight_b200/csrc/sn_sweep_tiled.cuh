@@ -1,7 +1,7 @@
 // sn_sweep_tiled.cuh -- the fast Metropolis sweep: TMA-staged shared-memory tiles.
 //
 // Replaces MC_moves -> MC_move -> site_energy (montecarlo-core.c:76-191) for
-// DipoleCutOff = 3 lattices with X, Y, Z >= 20 and Z a multiple of 4 (Z-slab handles: multiples of 32 planes); the last
+// DipoleCutOff = 3 (or 2) lattices with X, Y, Z >= 20 and Z a multiple of 4 (Z-slab handles: multiples of 32 planes); the last
 // tile of an axis may be partial, an odd number of tiles along an axis gets a third tile colour.
 //
 // Decomposition
@@ -136,9 +136,11 @@ __device__ __forceinline__ float2 sn_fma2(float2 a, float2 b, float2 c) { return
 // its neighbours a1 / b1 are the planes after a0 / b0).  T(r) = T(-r): the two moments are added first and the
 // tensor applied once.  ZPAIR: (a0.z, a1.z) and (b0.z, b1.z) are register pairs as loaded (one LDS.64 each),
 // so their sum is one FADD2; otherwise two FADDs write the halves of the pair.
-template <int DX, int DY, int DZ, bool SPECIES, bool ZPAIR>
+template <int DX, int DY, int DZ, bool SPECIES, bool ZPAIR, int CUT>
 __device__ __forceinline__ void sn_accumulate_pair2(SnAcc2 &A, const float4 a0, const float4 b0, const float4 a1, const float4 b1)
 {
+    if constexpr (DX * DX + DY * DY + DZ * DZ > CUT * CUT) return;      // beyond the handle's DipoleCutOff (the tile's halo is always 3 wide)
+    else {
     constexpr float txx = sn_T(DX, DY, DZ, 0, 0), tyy = sn_T(DX, DY, DZ, 1, 1), tzz = sn_T(DX, DY, DZ, 2, 2);
     constexpr float txy = sn_T(DX, DY, DZ, 0, 1), txz = sn_T(DX, DY, DZ, 0, 2), tyz = sn_T(DX, DY, DZ, 1, 2);
     float2 axy[2], az;
@@ -173,6 +175,7 @@ __device__ __forceinline__ void sn_accumulate_pair2(SnAcc2 &A, const float4 a0, 
         } else {
             A.gxy[0] = sn_add2(A.gxy[0], axy[0]); A.gxy[1] = sn_add2(A.gxy[1], axy[1]); A.gz = sn_add2(A.gz, az);
         }
+    }
     }
 }
 
@@ -232,7 +235,7 @@ __device__ __forceinline__ void sn_tile_load_pair(const SnTileCol &tc, float4 (&
     sn_tile_load_col<-C, M, SPECIES>(tc, wm);
 }
 
-template <int IDX, bool SPECIES>
+template <int IDX, bool SPECIES, int CUT>
 __device__ __forceinline__ void sn_tile_compute_pair(const float4 (&wp)[6], const float4 (&wm)[6], SnAcc2 &A)
 {
     constexpr snt::Col c = snt::col(IDX);
@@ -246,7 +249,7 @@ __device__ __forceinline__ void sn_tile_compute_pair(const float4 (&wp)[6], cons
             if constexpr (DZ == 0 || (S == 0 && DZ < 0) || (S == 1 && DZ > 0)) { A.d[S].x += wp[S + DZ + M].x; A.d[S].y += wm[S - DZ + M].y; }
         });
 #else
-        sn_accumulate_pair2<c.dx, c.dy, DZ, SPECIES, (DZ % 2 == 0)>(A, wp[DZ + M], wm[M - DZ], wp[1 + DZ + M], wm[1 - DZ + M]);
+        sn_accumulate_pair2<c.dx, c.dy, DZ, SPECIES, (DZ % 2 == 0), CUT>(A, wp[DZ + M], wm[M - DZ], wp[1 + DZ + M], wm[1 - DZ + M]);
 #endif
     });
 }
@@ -260,7 +263,7 @@ __host__ __device__ constexpr int next_in(unsigned mask, int idx)
 }
 }  // namespace snt
 
-template <unsigned MASK, int IDX, bool SPECIES>
+template <unsigned MASK, int IDX, bool SPECIES, int CUT>
 __device__ __forceinline__ void sn_tile_gather_chain(const SnTileCol &tc, SnAcc2 &A, float4 (&c0)[6], float4 (&c1)[6])
 {
     // c0/c1 hold pair IDX (already loaded); load the next pair of the mask, then do the arithmetic of this one
@@ -268,13 +271,13 @@ __device__ __forceinline__ void sn_tile_gather_chain(const SnTileCol &tc, SnAcc2
         constexpr int NEXT = snt::next_in(MASK, IDX + 1);
         float4 n0[6], n1[6];
         if constexpr (NEXT < snt::NCOL) sn_tile_load_pair<NEXT, SPECIES>(tc, n0, n1);
-        sn_tile_compute_pair<IDX, SPECIES>(c0, c1, A);
-        if constexpr (NEXT < snt::NCOL) sn_tile_gather_chain<MASK, NEXT, SPECIES>(tc, A, n0, n1);
+        sn_tile_compute_pair<IDX, SPECIES, CUT>(c0, c1, A);
+        if constexpr (NEXT < snt::NCOL) sn_tile_gather_chain<MASK, NEXT, SPECIES, CUT>(tc, A, n0, n1);
     }
 }
 
 // Same, with the loads running two column pairs ahead of the arithmetic (SN_EXP_DEPTH2)
-template <unsigned MASK, int IDX, bool SPECIES>
+template <unsigned MASK, int IDX, bool SPECIES, int CUT>
 __device__ __forceinline__ void sn_tile_gather_chain2(const SnTileCol &tc, SnAcc2 &A, float4 (&c0)[6], float4 (&c1)[6], float4 (&n0)[6], float4 (&n1)[6])
 {
     if constexpr (IDX < snt::NCOL) {
@@ -282,8 +285,8 @@ __device__ __forceinline__ void sn_tile_gather_chain2(const SnTileCol &tc, SnAcc
         constexpr int N2 = N1 < snt::NCOL ? snt::next_in(MASK, N1 + 1) : snt::NCOL;
         float4 m0[6], m1[6];
         if constexpr (N2 < snt::NCOL) sn_tile_load_pair<N2, SPECIES>(tc, m0, m1);
-        sn_tile_compute_pair<IDX, SPECIES>(c0, c1, A);
-        if constexpr (N1 < snt::NCOL) sn_tile_gather_chain2<MASK, N1, SPECIES>(tc, A, n0, n1, m0, m1);
+        sn_tile_compute_pair<IDX, SPECIES, CUT>(c0, c1, A);
+        if constexpr (N1 < snt::NCOL) sn_tile_gather_chain2<MASK, N1, SPECIES, CUT>(tc, A, n0, n1, m0, m1);
     }
 }
 
@@ -292,7 +295,7 @@ __device__ __forceinline__ void sn_tile_gather_chain2(const SnTileCol &tc, SnAcc
 // own two sites; a neighbour column is a compile-time immediate away.  Each
 // column pair (+c, -c) is loaded once for both sites (sliding z window) and combined with the
 // pair symmetry.  The loads of the next pair are issued before the arithmetic of the current one.
-template <unsigned MASK, bool CENTRE, bool SPECIES>
+template <unsigned MASK, bool CENTRE, bool SPECIES, int CUT>
 __device__ __forceinline__ void sn_tile_gather2(const SnTileCol &tc, float3 (&F)[2], float3 (&G)[2], float4 (&old)[2])
 {
     SnAcc2 A;
@@ -307,9 +310,9 @@ __device__ __forceinline__ void sn_tile_gather2(const SnTileCol &tc, float3 (&F)
         constexpr int SECOND = snt::next_in(MASK, FIRST + 1);
         float4 n0[6], n1[6];
         if constexpr (SECOND < snt::NCOL) sn_tile_load_pair<SECOND, SPECIES>(tc, n0, n1);
-        sn_tile_gather_chain2<MASK, FIRST, SPECIES>(tc, A, c0, c1, n0, n1);
+        sn_tile_gather_chain2<MASK, FIRST, SPECIES, CUT>(tc, A, c0, c1, n0, n1);
 #else
-        sn_tile_gather_chain<MASK, FIRST, SPECIES>(tc, A, c0, c1);
+        sn_tile_gather_chain<MASK, FIRST, SPECIES, CUT>(tc, A, c0, c1);
 #endif
     }
     if constexpr (CENTRE) {
@@ -318,9 +321,9 @@ __device__ __forceinline__ void sn_tile_gather2(const SnTileCol &tc, float3 (&F)
         sn_tile_load_col<0, 3, SPECIES>(tc, w);
         const float4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], w6 = w[6], w7 = w[7];
         old[0] = w3; old[1] = w4;
-        sn_accumulate_pair2<0, 0, 1, SPECIES, false>(A, w4, w2, w5, w3);
-        sn_accumulate_pair2<0, 0, 2, SPECIES, true>(A, w5, w1, w6, w2);
-        sn_accumulate_pair2<0, 0, 3, SPECIES, false>(A, w6, w0, w7, w1);
+        sn_accumulate_pair2<0, 0, 1, SPECIES, false, CUT>(A, w4, w2, w5, w3);
+        sn_accumulate_pair2<0, 0, 2, SPECIES, true, CUT>(A, w5, w1, w6, w2);
+        sn_accumulate_pair2<0, 0, 3, SPECIES, false, CUT>(A, w6, w0, w7, w1);
     }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
@@ -506,7 +509,7 @@ __device__ __forceinline__ void sn_tile_publish(const SnTileFlow &f, const SnTil
 
 // AUDIT: every attempt also leaves a record (proposal, accept uniform, the dE the chain used, decision, group
 // ordinal) for sn_mc_sweep_audit; the arithmetic and the order are those of the product instantiation.
-template <bool SPECIES, bool AUDIT>
+template <bool SPECIES, bool AUDIT, int CUT>
 __global__ void __launch_bounds__(snt::THREADS, 1)
 sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, const SnTileFlow fl)
 {
@@ -559,14 +562,15 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
         constexpr int BYTES = snt::XY_BYTES + snt::Z_BYTES + (SPECIES ? snt::Z_BYTES : 0);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
         // tensor = (floats of one z row, padded y, padded x, replica); the 28-plane window of a tile at z0 starts at
-        // row position z0 (plane z0 - 4); halo x0-3 / y0-3 -> padded x0 / y0
+        // row position z0 (plane z0 - 4); halo x0-3 / y0-3 -> padded x0 / y0 for cut-off 3; with a smaller cut-off the ghost shell
+        // is narrower than the halo and the box starts outside the array (zero fill; those cells carry zero tensors anyway)
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                     ::"r"(sn_smem_u32(smem)), "l"(&maps.xy), "r"(2 * it.z0), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
+                     ::"r"(sn_smem_u32(smem)), "l"(&maps.xy), "r"(2 * it.z0), "r"(it.y0 + G.g - snt::H), "r"(it.x0 + G.g - snt::H), "r"(it.rep), "r"(bar) : "memory");
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                     ::"r"(sn_smem_u32(smem + snt::OFF_Z)), "l"(&maps.z), "r"(it.z0), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
+                     ::"r"(sn_smem_u32(smem + snt::OFF_Z)), "l"(&maps.z), "r"(it.z0), "r"(it.y0 + G.g - snt::H), "r"(it.x0 + G.g - snt::H), "r"(it.rep), "r"(bar) : "memory");
         if constexpr (SPECIES)
             asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                         ::"r"(sn_smem_u32(smem + snt::OFF_L)), "l"(&maps.l), "r"(it.z0), "r"(it.y0), "r"(it.x0), "r"(it.rep), "r"(bar) : "memory");
+                         ::"r"(sn_smem_u32(smem + snt::OFF_L)), "l"(&maps.l), "r"(it.z0), "r"(it.y0 + G.g - snt::H), "r"(it.x0 + G.g - snt::H), "r"(it.rep), "r"(bar) : "memory");
     };
     // Block-wide rendezvous of the control warp and the workers.  They meet from different places in the code, so this
     // is a named barrier with an explicit thread count (bar.sync 2, THREADS), not __syncthreads().
@@ -703,9 +707,9 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
             float3 F[2], Gc[2];
             float4 old[2];
 #ifdef SN_EXP_NOGB
-            sn_tile_gather2<0u, false, SPECIES>(tc, F, Gc, old);
+            sn_tile_gather2<0u, false, SPECIES, CUT>(tc, F, Gc, old);
 #else
-            sn_tile_gather2<snt::MASK_B, false, SPECIES>(tc, F, Gc, old);
+            sn_tile_gather2<snt::MASK_B, false, SPECIES, CUT>(tc, F, Gc, old);
 #endif
             float2 *dst = xF + (sp & 1) * 3 * snt::SITE_THREADS + tl;
             dst[0 * snt::SITE_THREADS] = make_float2(F[0].x, F[0].y);
@@ -727,9 +731,9 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
                 float3 F[2], Gc[2];
                 float4 old[2];
 #ifdef SN_EXP_NOGA
-                sn_tile_gather2<0u, true, SPECIES>(tc, F, Gc, old);
+                sn_tile_gather2<0u, true, SPECIES, CUT>(tc, F, Gc, old);
 #else
-                sn_tile_gather2<snt::MASK_A, true, SPECIES>(tc, F, Gc, old);
+                sn_tile_gather2<snt::MASK_A, true, SPECIES, CUT>(tc, F, Gc, old);
 #endif
                 {
                     const float2 *src = xF + (sp & 1) * 3 * snt::SITE_THREADS + tl;
@@ -774,8 +778,8 @@ sn_tiled_kernel(const __grid_constant__ SnTileMaps maps, const SnSweepArgs a, co
 #pragma unroll
                     for (int t2 = 0; t2 < t4; t2++) {
                         const int d1 = t4 - t2, d2 = 4 + t2 - t4;      // distance to the earlier site below / in the segment above
-                        const float w1 = d1 == 1 ? 1.0f : d1 == 2 ? 0.125f : (1.0f / 27.0f);
-                        const float w2 = d2 == 1 ? 1.0f : d2 == 2 ? 0.125f : (1.0f / 27.0f);
+                        const float w1 = d1 > CUT ? 0.0f : d1 == 1 ? 1.0f : d1 == 2 ? 0.125f : (1.0f / 27.0f);     // beyond the cut-off: no interaction
+                        const float w2 = d2 > CUT ? 0.0f : d2 == 1 ? 1.0f : d2 == 2 ? 0.125f : (1.0f / 27.0f);
                         dE = fmaf(w1, q[s].x * dmS[t2].x + q[s].y * dmS[t2].y + q[s].z * dmS[t2].z, dE);
                         dE = fmaf(w2, q[s].x * dmU[t2].x + q[s].y * dmU[t2].y + q[s].z * dmU[t2].z, dE);
                         if (d1 == 1) dE += cg[s].x * dpS[t2].x + cg[s].y * dpS[t2].y + cg[s].z * dpS[t2].z;
@@ -901,7 +905,7 @@ bool sn_tiled_supported(const sn_handle *h, std::string *why)
 {
     const SnGeom &G = h->G;
     const char *msg = nullptr;
-    if (h->p.cutoff != 3) msg = "DipoleCutOff must be 3";
+    if (h->p.cutoff != 3 && h->p.cutoff != 2) msg = "DipoleCutOff must be 2 or 3";
     else if (G.Z == 1) msg = "lattice is flat (Z == 1)";
     // two tiles per axis at least, and a tile's box must not hold images of the tile's own sites: the lower halo of the
     // first tile shows the sites X-3 .. X-1, which must lie beyond its 16 own columns (X >= 19)
@@ -941,10 +945,10 @@ int sn_tiled_prepare(sn_handle *h)
         if (r != CUDA_SUCCESS) { delete tm; return sn_fail(SN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r); }
     }
     h->tmap = tm;
-    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
-    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
-    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
-    SN_CUDA_CHECK(cudaFuncSetAttribute(sn_tiled_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
+    for (const void *k : {(const void *)sn_tiled_kernel<true, false, 3>, (const void *)sn_tiled_kernel<false, false, 3>, (const void *)sn_tiled_kernel<true, true, 3>,
+                          (const void *)sn_tiled_kernel<false, true, 3>, (const void *)sn_tiled_kernel<true, false, 2>, (const void *)sn_tiled_kernel<false, false, 2>,
+                          (const void *)sn_tiled_kernel<true, true, 2>, (const void *)sn_tiled_kernel<false, true, 2>})
+        SN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, snt::SMEM_BYTES));
     return SN_OK;
 }
 
@@ -1044,11 +1048,16 @@ int sn_sweep_tiled_launch(sn_handle *h, long long nsweeps, long long *launches)
         SN_CUDA_CHECK(cudaMemsetAsync(f.next, 0, sizeof(unsigned long long), h->stream));
         const int sms = h->grid_limit > 0 ? std::min(h->grid_limit, h->num_sms) : h->num_sms;
         const int grid = (int)std::min<unsigned long long>(n1 - n0, (unsigned long long)sms);
-        if (f.audit) {
-            if (h->species) sn_tiled_kernel<true, true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
-            else sn_tiled_kernel<false, true><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
-        } else if (h->species) sn_tiled_kernel<true, false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
-        else sn_tiled_kernel<false, false><<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f);
+        auto go = [&](auto kern) { kern<<<grid, snt::THREADS, snt::SMEM_BYTES, h->stream>>>(tm, a, f); };
+        if (h->p.cutoff == 3) {
+            if (f.audit) { if (h->species) go(sn_tiled_kernel<true, true, 3>); else go(sn_tiled_kernel<false, true, 3>); }
+            else if (h->species) go(sn_tiled_kernel<true, false, 3>);
+            else go(sn_tiled_kernel<false, false, 3>);
+        } else {
+            if (f.audit) { if (h->species) go(sn_tiled_kernel<true, true, 2>); else go(sn_tiled_kernel<false, true, 2>); }
+            else if (h->species) go(sn_tiled_kernel<true, false, 2>);
+            else go(sn_tiled_kernel<false, false, 2>);
+        }
         if (launches) (*launches)++;
         return SN_OK;
     };

@@ -148,22 +148,24 @@ CASES = [
     ("odd tile counts", (48, 32, 48), ((1.0, 0.5, 0.0), (0.6, 0.3, 0.1)), 0.0, (0.02, 0.0, 0.0), False, 3, 300),   # 3 x 2 x 3 tiles: 18 phases
     ("partial tiles", (40, 35, 44), ((1.0, 0.5, 0.0), (0.6, 0.3, 0.1)), 0.3, (0.02, -0.01, 0.0), False, 3, 300),     # 3 x 3 x 3 tiles, the last of every axis cut
     ("two small tiles", (20, 27, 24), ((1.0, 0.5, 0.0), (0.6, 0.3, 0.1)), 0.0, (0.02, 0.0, 0.01), False, 3, 300),     # 2 x 2 x 2 tiles, 16 + a few cells per axis
+    ("cut-off 2", (32, 48, 32), ((1.0, 0.5, 0.0), (0.6, 0.3, 0.1)), 0.4, (0.02, 0.0, -0.01), False, 3, 300, 2),       # DipoleCutOff = 2: 32 neighbours, ghost shell of 2
 ]
 
 
 @pytest.mark.parametrize("kernel", ["tiled", "tiled_phased", "colour"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_every_attempt_matches_the_reference(sn, case, kernel):
-    name, (X, Y, Z), species, K, E, constrain, dim, T = case
+    name, (X, Y, Z), species, K, E, constrain, dim, T = case[:8]
+    cutoff = case[8] if len(case) > 8 else 3
     kern = {"tiled": sn.SN_KERNEL_TILED, "tiled_phased": sn.SN_KERNEL_TILED_PHASED, "colour": sn.SN_KERNEL_COLOUR}[kernel]
-    if kernel != "tiled" and name not in ("species + vacancies", "K and field", "odd tile counts"):
+    if kernel != "tiled" and name not in ("species + vacancies", "K and field", "odd tile counts", "cut-off 2"):
         pytest.skip("the phased launch and the colour passes are audited on two cases")
     E = tuple(float(np.float32(v)) for v in E)
     lengths, prev = species if species else ((1.0,), (1.0,))
     reps, seed, cage = 2, 0xDEADBEEF + T, (1.0, 2.0)
     lats = [oa.random_lattice(X, Y, Z, seed=80 + r, lengths=lengths, prevalence=prev) for r in range(reps)]
     beta = sn.beta_of_T(T)
-    with sn.Simulation(X, Y, Z, CageStrain=1.0, K=K, Efield=E, beta=beta, ConstrainToX=constrain, DIM=dim, nreplicas=reps,
+    with sn.Simulation(X, Y, Z, DipoleCutOff=cutoff, CageStrain=1.0, K=K, Efield=E, beta=beta, ConstrainToX=constrain, DIM=dim, nreplicas=reps,
                        seed=seed, kernel=kern) as sim:
         for r in range(reps):
             sim.set_lattice(lats[r], r)
@@ -176,7 +178,7 @@ def test_every_attempt_matches_the_reference(sn, case, kernel):
         c1 = [sim.counters(r) for r in range(reps)]
         assert sim.sweep_count() == 3
     for r in range(reps):
-        p = oa.make_params(X, Y, Z, 3, cage[r], K, E, beta, constrain, dim, T)
+        p = oa.make_params(X, Y, Z, cutoff, cage[r], K, E, beta, constrain, dim, T)
         worst, n_flip, n_live, ngroups = _replay(p, start[r], rec[r], final[r], f"{name} / {kernel} / replica {r}")
         flag = rec[r][..., 5]
         assert tuple(b - a for a, b in zip(c0[r], c1[r])) == (int((flag == 1).sum()), int((flag == 0).sum()), int((flag == 2).sum()))
@@ -184,7 +186,8 @@ def test_every_attempt_matches_the_reference(sn, case, kernel):
         if name in ("partial tiles", "two small tiles"):                        # a cut tile has no sites in some (cx, cy) classes: those groups are empty
             assert phases * 48 <= ngroups <= phases * 64
         else:
-            assert ngroups == (phases * 64 if kernel != "colour" else 64)
+            colour_groups = int(np.prod([(cutoff + 1) + n % (cutoff + 1) for n in (X, Y, Z)]))   # period cutoff + 1, leftover planes get colours of their own
+            assert ngroups == (phases * 64 if kernel != "colour" else colour_groups)
         # the random numbers behind the records
         npd, ua = _expected_draws("colour" if kernel == "colour" else "tiled", X, Y, Z, 0, seed, r << 8, 2, constrain, dim)
         live = flag != 2

@@ -287,6 +287,13 @@ def test_kernel_selection(sn, shape, want):
         assert sim.kernel_in_use() == ids[want]
 
 
+def test_kernel_selection_cutoff_2_runs_on_the_tiles_and_4_on_colour_passes(sn):
+    with sn.Simulation(64, 64, 64, DipoleCutOff=2) as sim:
+        assert sim.kernel_in_use() == sn.SN_KERNEL_TILED
+    with sn.Simulation(64, 64, 64, DipoleCutOff=4) as sim:
+        assert sim.kernel_in_use() == sn.SN_KERNEL_COLOUR
+
+
 def test_odd_tile_counts_match_the_colour_kernel_statistics(sn):
     """48^3 (3 tiles per axis, 27 tile phases) on the tiled kernel against colour passes: equilibrium energy and
     acceptance agree within error bars (independent seeds)."""
