@@ -6,13 +6,15 @@ import starrynight_b200 as sn
 
 which = sys.argv[1]
 X, Y, Z, kern = {"tiled": (64, 32, 32, sn.SN_KERNEL_TILED), "resident": (20, 20, 28, sn.SN_KERNEL_RESIDENT),
-                 "colour": (16, 12, 16, sn.SN_KERNEL_COLOUR)}[which]
+                 "colour": (16, 12, 16, sn.SN_KERNEL_COLOUR), "partial": (40, 35, 44, sn.SN_KERNEL_TILED),       # every axis ends in a cut tile
+                 "cut2": (32, 48, 32, sn.SN_KERNEL_TILED)}[which]                                                  # DipoleCutOff 2: box starts outside the array
+cutoff = 2 if which == "cut2" else 3
 rng = np.random.default_rng(3)
 lat = np.zeros((X, Y, Z, 4), np.float32)
 v = rng.standard_normal((X, Y, Z, 3)).astype(np.float32)
 lat[..., :3] = v / np.linalg.norm(v, axis=-1, keepdims=True)
 lat[..., 3] = rng.choice(np.array([1.0, 0.5, 0.0], np.float32), size=(X, Y, Z), p=[0.7, 0.2, 0.1])
-with sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.02, 0, 0), nreplicas=2, seed=11, kernel=kern) as sim:
+with sn.Simulation(X, Y, Z, DipoleCutOff=cutoff, CageStrain=1.0, Efield=(0.02, 0, 0), nreplicas=2, seed=11, kernel=kern) as sim:
     for r in range(2):
         sim.set_lattice(lat, r)
     sim.MC_sweeps(2)
