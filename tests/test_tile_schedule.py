@@ -58,3 +58,28 @@ def test_rejects_what_the_tiled_kernel_cannot_take(sn):
         sn.tile_schedule(16, 64, 64)
     with pytest.raises(sn.SnError):
         sn.tile_schedule(64, 64, 30)
+
+
+@pytest.mark.parametrize("shape", [(64, 32, 48), (48, 48, 48), (100, 44, 36), (20, 27, 24)])
+def test_every_dependency_precedes_its_item_in_the_global_order(sn, shape):
+    """The dataflow rule (sn_tile_deps_ready): an item (sweep s, phase p) waits until each neighbouring tile has completed
+    s + 1 sweeps if its phase q < p, else s sweeps.  Every such event must lie earlier in the global item order, or persistent
+    CTAs that take items in order could wait for work nobody has started (deadlock)."""
+    X, Y, Z = shape
+    tn = [(n + 15) // 16 for n in shape]
+    per_sweep = []
+    for s in range(3):
+        items = sn.tile_schedule(X, Y, Z, 1, sweep=s)
+        per_sweep.append({tuple(r[1:4]): (i, int(r[4])) for i, r in enumerate(items.tolist())})     # tile -> (position, phase)
+    S = len(per_sweep[0])
+    for s in (1, 2):
+        for tile, (pos, p) in per_sweep[s].items():
+            n_item = s * S + pos
+            for d in itertools.product((-1, 0, 1), repeat=3):
+                nb = tuple((tile[a] + d[a]) % tn[a] for a in range(3))
+                if nb == tile:
+                    continue
+                q = per_sweep[s][nb][1]
+                need_sweep = s if q < p else s - 1                   # the neighbour's item whose completion is awaited
+                n_dep = need_sweep * S + per_sweep[need_sweep][nb][0]
+                assert n_dep < n_item, f"tile {tile} (sweep {s}, phase {p}) waits for {nb} (phase {q}) which comes later in the order"
