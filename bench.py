@@ -488,7 +488,13 @@ def run_ours(args):
         # handles used in rotation.  Three were measured too (profiles/r02_bench_c5_n8_three_handles.json): no gain -- where the
         # copies outlast the sweeps (8 GPUs) the host side is saturated and the loop runs at the serial sum either way
         NH = 2
-        outs = [[torch.empty_like(host_of(r)).pin_memory() for r in range(reps)] for _ in range(NH)]
+        # replica batches travel as one dense block per direction (sn_set_lattices_async / sn_get_lattices_async)
+        batch = reps > 1
+        if batch:
+            host_all = torch.stack([host_of(r) for r in range(reps)]).pin_memory()
+            outs = [torch.empty_like(host_all).pin_memory() for _ in range(NH)]
+        else:
+            outs = [[torch.empty_like(host_of(r)).pin_memory() for r in range(reps)] for _ in range(NH)]
         h2d = sum(host_of(r).numel() * 4 for r in range(reps))
         d2h = h2d + 24 * reps
         sims = [sim] + [make_sim() for _ in range(NH - 1)]
@@ -503,14 +509,18 @@ def run_ours(args):
                 s.synchronize()                       # its previous download has landed: host buffers are free again
                 if i >= (NH if pipelined else 1):
                     s.counters()                      # the step's result: ACCEPT / REJECT (and the lattice in outs)
-                for r in range(reps):
-                    s.set_lattice_async(host_of(r).data_ptr(), r)     # H2D from pinned memory
+                if batch:
+                    s.set_lattices_async(host_all.data_ptr())         # H2D from pinned memory, every replica in one block
+                else:
+                    s.set_lattice_async(host_of(0).data_ptr(), 0)     # H2D from pinned memory
                 if o is not None:
                     s.order_after(o)                  # the handles' sweep kernels keep one order on every GPU
                 s.pull_ghosts()                       # slab ghost planes, device to device, handshake included
                 step(s, False)
-                for r in range(reps):
-                    s.get_lattice_async(outs[i % NH][r].data_ptr(), r)  # D2H
+                if batch:
+                    s.get_lattices_async(outs[i % NH].data_ptr())     # D2H
+                else:
+                    s.get_lattice_async(outs[i % NH][0].data_ptr(), 0)
             for s in (sims if pipelined else sims[:1]):
                 s.synchronize()
                 s.counters()

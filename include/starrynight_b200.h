@@ -113,6 +113,10 @@ SN_API int sn_get_lattice(sn_handle *h, int replica, float *xyzlen);
  * handles used alternately, one lattice travels over PCIe while the other is being swept (see sn_order_after). */
 SN_API int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzlen);
 SN_API int sn_get_lattice_async(sn_handle *h, int replica, float *xyzlen);
+/* `count` consecutive replicas at once, host block float[count][X][Y][nz][4]: one copy and one kernel for the whole batch
+ * (a T x CageStrain grid of small lattices would otherwise pay the per-call overhead a thousand times per step) */
+SN_API int sn_set_lattices_async(sn_handle *h, int first, int count, const float *xyzlen);
+SN_API int sn_get_lattices_async(sn_handle *h, int first, int count, float *xyzlen);
 /* h's later work waits (on the device) for the sweeps queued so far on `other`: fixes the order of the two handles'
  * persistent sweep kernels when they are used as a double buffer.  Z-slab handles that share a GPU normally split its
  * SMs (their kernels may have to be resident together); handles ordered this way never run at once and are given

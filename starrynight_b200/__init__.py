@@ -27,7 +27,7 @@ SN_RDF_BINS = 81
 
 EXPORTS = [
     "sn_last_error", "sn_version", "sn_device_count", "sn_default_params", "sn_create", "sn_destroy", "sn_neighbour_table",
-    "sn_set_lattice", "sn_get_lattice", "sn_set_lattice_async", "sn_get_lattice_async", "sn_order_after", "sn_pull_ghosts", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_set_replica_cagestrain", "sn_mc_sweeps", "sn_mc_sweep_audit",
+    "sn_set_lattice", "sn_get_lattice", "sn_set_lattice_async", "sn_get_lattice_async", "sn_set_lattices_async", "sn_get_lattices_async", "sn_order_after", "sn_pull_ghosts", "sn_set_beta", "sn_set_efield", "sn_set_cagestrain", "sn_set_replica_cagestrain", "sn_mc_sweeps", "sn_mc_sweep_audit",
     "sn_mc_sweeps_timed", "sn_synchronize", "sn_get_counters", "sn_reset_counters", "sn_set_counters",
     "sn_get_sweep_count", "sn_set_sweep_count", "sn_set_replica_seed", "sn_site_energy",
     "sn_total_energy", "sn_polarisation", "sn_landau_order", "sn_rdf", "sn_potential_map", "sn_efield_map", "sn_recombination", "sn_recombination_partial", "sn_recombination_finish", "sn_get_boundary",
@@ -70,6 +70,8 @@ def load_library() -> C.CDLL:
     lib.sn_get_lattice.argtypes = [H, C.c_int, C.c_void_p]
     lib.sn_set_lattice_async.argtypes = [H, C.c_int, C.c_void_p]
     lib.sn_get_lattice_async.argtypes = [H, C.c_int, C.c_void_p]
+    lib.sn_set_lattices_async.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    lib.sn_get_lattices_async.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.sn_order_after.argtypes = [H, H]
     lib.sn_pull_ghosts.argtypes = [H]
     lib.sn_set_beta.argtypes = [H, C.c_int, C.c_double]
@@ -233,6 +235,13 @@ class Simulation:
 
     def get_lattice_async(self, ptr, replica=0):
         _check(self.lib.sn_get_lattice_async(self.h, replica, C.c_void_p(ptr)))
+
+    def set_lattices_async(self, ptr, first=0, count=None):
+        """Queue the upload of `count` consecutive replicas from one dense pinned block float[count][X][Y][nz][4]."""
+        _check(self.lib.sn_set_lattices_async(self.h, first, self.nreplicas - first if count is None else count, C.c_void_p(ptr)))
+
+    def get_lattices_async(self, ptr, first=0, count=None):
+        _check(self.lib.sn_get_lattices_async(self.h, first, self.nreplicas - first if count is None else count, C.c_void_p(ptr)))
 
     def order_after(self, other: "Simulation"):
         _check(self.lib.sn_order_after(self.h, other.h))

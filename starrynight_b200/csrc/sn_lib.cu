@@ -344,9 +344,13 @@ int sn_refresh_ghosts(sn_handle *h)
 // noting whether the replica carries species (any length != 1).  No strided copies, no separate ghost refresh, no
 // round trip through the canonical array, no host synchronisation.
 template <bool TILED>
-__global__ void __launch_bounds__(256) sn_scatter_kernel(const float4 *__restrict__ staging, float4 *__restrict__ dst, const SnGeom G,
-                                                         unsigned int *__restrict__ species_flag)
+__global__ void __launch_bounds__(256) sn_scatter_kernel(const float4 *__restrict__ staging0, float4 *__restrict__ dst0, const SnGeom G,
+                                                         unsigned int *__restrict__ species_flag0, const long long rep_stride)
 {
+    // blockIdx.y: replica of the batch (staging dense, the destination rep_stride cells apart)
+    const float4 *__restrict__ staging = staging0 + (long long)blockIdx.y * G.X * G.Y * G.nz;
+    float4 *__restrict__ dst = dst0 + (long long)blockIdx.y * rep_stride;
+    unsigned int *__restrict__ species_flag = species_flag0 + blockIdx.y;
     // one thread per padded cell (ghost shell included); z ghosts of a Z-slab handle belong to the neighbours
     // (sn_pull_ghosts / sn_set_ghost) and are left alone
     const long long cells = (long long)(G.X + 2 * G.g) * G.PY * G.PZ;
@@ -368,8 +372,10 @@ __global__ void __launch_bounds__(256) sn_scatter_kernel(const float4 *__restric
 }
 
 template <bool TILED>
-__global__ void __launch_bounds__(256) sn_gather_kernel(const float4 *__restrict__ src, float4 *__restrict__ staging, const SnGeom G)
+__global__ void __launch_bounds__(256) sn_gather_kernel(const float4 *__restrict__ src0, float4 *__restrict__ staging0, const SnGeom G, const long long rep_stride)
 {
+    const float4 *__restrict__ src = src0 + (long long)blockIdx.y * rep_stride;
+    float4 *__restrict__ staging = staging0 + (long long)blockIdx.y * G.X * G.Y * G.nz;
     const long long n = (long long)G.X * G.Y * G.nz;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int z = (int)(i % G.nz), y = (int)((i / G.nz) % G.Y), x = (int)(i / ((long long)G.nz * G.Y));
@@ -377,9 +383,9 @@ __global__ void __launch_bounds__(256) sn_gather_kernel(const float4 *__restrict
     }
 }
 
-static int sn_staging(sn_handle *h, float4 **out)
+static int sn_staging(sn_handle *h, float4 **out, int count = 1)
 {
-    const size_t bytes = (size_t)h->G.X * h->G.Y * h->G.nz * sizeof(float4);
+    const size_t bytes = (size_t)h->G.X * h->G.Y * h->G.nz * sizeof(float4) * (size_t)count;
     if (bytes > h->staging_bytes) {
         if (h->staging) cudaFree(h->staging);
         h->staging = nullptr; h->staging_bytes = 0;
@@ -404,26 +410,29 @@ int sn_resolve_species(sn_handle *h)
     return SN_OK;
 }
 
-extern "C" int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzlen)
+// `count` consecutive replicas from one dense host block: ONE copy, ONE scatter launch (replica along grid.y)
+extern "C" int sn_set_lattices_async(sn_handle *h, int first, int count, const float *xyzlen)
 {
-    SN_CHECK_HANDLE(h, replica);
+    SN_CHECK_HANDLE(h, first);
     if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_set_lattice: null buffer");
+    if (count < 1 || first + count > h->p.nreplicas) return sn_fail(SN_ERR_INVALID, "sn_set_lattices: replicas [%d, %d) of %d", first, first + count, h->p.nreplicas);
     const SnGeom &G = h->G;
-    float4 *stg; int rc = sn_staging(h, &stg);
+    float4 *stg; int rc = sn_staging(h, &stg, count);
     if (rc) return rc;
-    const size_t bytes = (size_t)G.X * G.Y * G.nz * sizeof(float4);
+    const size_t bytes = (size_t)G.X * G.Y * G.nz * sizeof(float4) * (size_t)count;
     SN_CUDA_CHECK(cudaMemcpyAsync(stg, xyzlen, bytes, cudaMemcpyHostToDevice, h->stream));
-    SN_CUDA_CHECK(cudaMemsetAsync(h->rep_species_dev + replica, 0, sizeof(unsigned int), h->stream));
+    SN_CUDA_CHECK(cudaMemsetAsync(h->rep_species_dev + first, 0, sizeof(unsigned int) * count, h->stream));
     const long long cells = G.rep_stride;
-    const int nblocks = (int)std::min<long long>((cells + 255) / 256, (long long)h->num_sms * 16);
+    const int nbx = (int)std::min<long long>((cells + 255) / 256, std::max<long long>(1, (long long)h->num_sms * 16 / count));
+    const dim3 grid((unsigned)nbx, (unsigned)count);
     if (h->use_tiled) {
         // straight into the tiled kernel's copy; other replicas that only live in the canonical array come along first
-        if (!h->lat2_valid && h->p.nreplicas > 1 && (rc = sn_convert_layout(h, true))) return rc;
-        sn_scatter_kernel<true><<<nblocks, 256, 0, h->stream>>>(stg, h->lat2 + (long long)replica * sn_rep_stride2(G), G, h->rep_species_dev + replica);
+        if (!h->lat2_valid && h->p.nreplicas > count && (rc = sn_convert_layout(h, true))) return rc;
+        sn_scatter_kernel<true><<<grid, 256, 0, h->stream>>>(stg, h->lat2 + (long long)first * sn_rep_stride2(G), G, h->rep_species_dev + first, sn_rep_stride2(G));
         h->lat2_valid = true; h->lat_valid = false;
     } else {
         if ((rc = sn_sync_canonical(h))) return rc;
-        sn_scatter_kernel<false><<<nblocks, 256, 0, h->stream>>>(stg, h->lat + (long long)replica * G.rep_stride, G, h->rep_species_dev + replica);
+        sn_scatter_kernel<false><<<grid, 256, 0, h->stream>>>(stg, h->lat + (long long)first * G.rep_stride, G, h->rep_species_dev + first, G.rep_stride);
         h->lat_valid = true; h->lat2_valid = false;
     }
     SN_CUDA_CHECK(cudaGetLastError());
@@ -431,6 +440,11 @@ extern "C" int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzl
     SN_CUDA_CHECK(cudaEventRecord(h->ev_species, h->stream));
     h->species_dirty = true;
     return SN_OK;
+}
+
+extern "C" int sn_set_lattice_async(sn_handle *h, int replica, const float *xyzlen)
+{
+    return sn_set_lattices_async(h, replica, 1, xyzlen);
 }
 
 extern "C" int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen)
@@ -441,23 +455,30 @@ extern "C" int sn_set_lattice(sn_handle *h, int replica, const float *xyzlen)
     return SN_OK;
 }
 
-extern "C" int sn_get_lattice_async(sn_handle *h, int replica, float *xyzlen)
+extern "C" int sn_get_lattices_async(sn_handle *h, int first, int count, float *xyzlen)
 {
-    SN_CHECK_HANDLE(h, replica);
+    SN_CHECK_HANDLE(h, first);
     if (!xyzlen) return sn_fail(SN_ERR_INVALID, "sn_get_lattice: null buffer");
+    if (count < 1 || first + count > h->p.nreplicas) return sn_fail(SN_ERR_INVALID, "sn_get_lattices: replicas [%d, %d) of %d", first, first + count, h->p.nreplicas);
     const SnGeom &G = h->G;
-    float4 *stg; int rc = sn_staging(h, &stg);
+    float4 *stg; int rc = sn_staging(h, &stg, count);
     if (rc) return rc;
     const long long n = (long long)G.X * G.Y * G.nz;
-    const int nblocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 16);
-    if (h->use_tiled && h->lat2_valid) sn_gather_kernel<true><<<nblocks, 256, 0, h->stream>>>(h->lat2 + (long long)replica * sn_rep_stride2(G), stg, G);
+    const int nbx = (int)std::min<long long>((n + 255) / 256, std::max<long long>(1, (long long)h->num_sms * 16 / count));
+    const dim3 grid((unsigned)nbx, (unsigned)count);
+    if (h->use_tiled && h->lat2_valid) sn_gather_kernel<true><<<grid, 256, 0, h->stream>>>(h->lat2 + (long long)first * sn_rep_stride2(G), stg, G, sn_rep_stride2(G));
     else {
         if ((rc = sn_sync_canonical(h))) return rc;
-        sn_gather_kernel<false><<<nblocks, 256, 0, h->stream>>>(h->lat + (long long)replica * G.rep_stride, stg, G);
+        sn_gather_kernel<false><<<grid, 256, 0, h->stream>>>(h->lat + (long long)first * G.rep_stride, stg, G, G.rep_stride);
     }
     SN_CUDA_CHECK(cudaGetLastError());
-    SN_CUDA_CHECK(cudaMemcpyAsync(xyzlen, stg, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    SN_CUDA_CHECK(cudaMemcpyAsync(xyzlen, stg, (size_t)n * sizeof(float4) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
     return SN_OK;
+}
+
+extern "C" int sn_get_lattice_async(sn_handle *h, int replica, float *xyzlen)
+{
+    return sn_get_lattices_async(h, replica, 1, xyzlen);
 }
 
 extern "C" int sn_get_lattice(sn_handle *h, int replica, float *xyzlen)

@@ -495,3 +495,37 @@ def test_async_double_buffer_equals_synchronous_calls(sn, shape, kernel):
         s.close()
     for i in range(4):
         assert np.array_equal(dst[i].numpy(), want[i]), f"batch {i}"
+
+
+@pytest.mark.parametrize("shape,kernel", [((24, 20, 1), "auto"), ((32, 32, 32), "tiled"), ((16, 12, 8), "colour")])
+def test_batched_replica_transfer_equals_one_call_per_replica(sn, shape, kernel):
+    """sn_set_lattices_async / sn_get_lattices_async move a whole replica batch with one copy and one kernel; the chain
+    that follows must be the one the per-replica calls give, species flags included."""
+    import torch
+    X, Y, Z = shape
+    reps = 5
+    kid = {"auto": sn.SN_KERNEL_AUTO, "tiled": sn.SN_KERNEL_TILED, "colour": sn.SN_KERNEL_COLOUR}[kernel]
+    lats = [oa.random_lattice(X, Y, Z, seed=60 + r, lengths=(1.0, 0.5, 0.0) if r % 2 else (1.0,), prevalence=(0.6, 0.3, 0.1) if r % 2 else (1.0,)) for r in range(reps)]
+    block = torch.from_numpy(np.stack(lats)).pin_memory()
+    out = torch.empty_like(block).pin_memory()
+    res = []
+    for batched in (False, True):
+        with sn.Simulation(X, Y, Z, CageStrain=1.0, Efield=(0.02, 0, 0), nreplicas=reps, seed=9, kernel=kid) as sim:
+            if batched:
+                sim.set_lattices_async(block.data_ptr())
+            else:
+                for r in range(reps):
+                    sim.set_lattice(lats[r], r)
+            sim.MC_sweeps(3)
+            if batched:
+                sim.get_lattices_async(out.data_ptr()); sim.synchronize()
+                got = [out[r].numpy().copy() for r in range(reps)]
+                # a partial batch in the middle
+                sim.get_lattices_async(out.data_ptr(), 1, 3); sim.synchronize()
+                assert all(np.array_equal(out[k].numpy(), got[1 + k]) for k in range(3))
+            else:
+                got = [sim.get_lattice(r) for r in range(reps)]
+            res.append((got, [sim.counters(r) for r in range(reps)]))
+    for r in range(reps):
+        assert np.array_equal(res[0][0][r], res[1][0][r]), f"replica {r}: batched transfer changed the chain"
+        assert res[0][1][r] == res[1][1][r]
